@@ -1,0 +1,178 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (build container only).
+
+TEST INFRASTRUCTURE ONLY.  Usage:  python -m oracle.gen_golden
+The reference has no tests or golden vectors of its own, so these
+fixtures -- outputs of the reference's own code on seeded synthetic inputs -- are what pins
+the oracle (tests/test_oracle.py) and, through it, the CUDA path.
+
+Generated with torch 2.11.0 (CPU), numba 0.65.0, numpy 2.3.5.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import refharness  # noqa: E402
+from yoloseries_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _pack_outputs(outs):
+    """list[ndarray(K,6) | None] -> (rows (b, Kmax, 6), counts (b,), -1 == None)."""
+    kmax = max([o.shape[0] for o in outs if o is not None] + [1])
+    rows = np.zeros((len(outs), kmax, 6), dtype=np.float32)
+    cnt = np.zeros(len(outs), dtype=np.int32)
+    for i, o in enumerate(outs):
+        if o is None:
+            cnt[i] = -1
+        else:
+            cnt[i] = o.shape[0]
+            rows[i, : o.shape[0]] = o
+    return rows, cnt
+
+
+def _clone(x):
+    if isinstance(x, torch.Tensor):
+        return x.clone()
+    if isinstance(x, (list, tuple)):
+        return type(x)(_clone(v) for v in x)
+    if isinstance(x, dict):
+        return type(x)((k, _clone(v)) for k, v in x.items())
+    return x
+
+
+def _flat_np(prefix, heads, store):
+    if isinstance(heads, torch.Tensor):
+        store[prefix] = heads.numpy()
+    else:
+        for i, h in enumerate(heads):
+            _flat_np(f"{prefix}_{i}", h, store)
+
+
+def evaluator_case(trainer, family, dist, img, batch, seed, C=80, **hyp_over):
+    from collections import OrderedDict
+
+    hyp = refharness.reference_hyp((img, img), num_class=C, **hyp_over)
+    heads = synth.make_heads(family, batch, img, img, C, dist, seed, "cpu")
+    dummy = torch.zeros(batch, 3, img, img)
+    anchors = torch.tensor(synth.V5_ANCHORS_PX)
+    # the reference mutates model outputs in place for v7 / retinanet: hand it clones
+    if family == "yolov5":
+        ev = trainer.YOLOV5Evaluator(lambda x: _clone(heads), anchors, hyp, compute_metric=True)
+    elif family == "yolov7":
+        ev = trainer.YOLOV7Evaluator(lambda x: OrderedDict((f"p{i}", h.clone()) for i, h in enumerate(heads)),
+                                     anchors, hyp, compute_metric=True)
+    elif family == "yolox":
+        ev = trainer.YOLOXEvaluator(lambda x: OrderedDict((f"p{i}", h.clone()) for i, h in enumerate(heads)),
+                                    hyp, compute_metric=True)
+    elif family == "yolov8":
+        ev = trainer.YOLOV8Evaluator(lambda x: OrderedDict((f"p{i}", h.clone()) for i, h in enumerate(heads)),
+                                     hyp, compute_metric=True)
+    elif family == "retinanet":
+        ev = trainer.RetinaNetEvaluator(lambda x: _clone(heads), hyp, compute_metric=True)
+    elif family == "retinanet_exp":
+        ev = trainer.RetinaNetEvaluatorExperiment(lambda x: _clone(heads), hyp, compute_metric=True)
+    elif family == "fcos":
+        ev = trainer.FCOSEvaluator(lambda x: _clone(heads), hyp, compute_metric=True)
+    else:
+        raise ValueError(family)
+    decoded = ev.do_inference(dummy)
+    outs = ev.numba_nms(decoded.clone())
+    rows, cnt = _pack_outputs(outs)
+    store = {"decoded": decoded.numpy().astype(np.float32), "rows": rows, "counts": cnt}
+    _flat_np("head", heads, store)
+    meta = dict(family=family, dist=dist, img=img, batch=batch, seed=seed, num_class=C)
+    meta.update({k: v for k, v in hyp.items() if isinstance(v, (int, float, bool, str))})
+    store["meta"] = np.array(repr(meta))
+    return store
+
+
+def utils_case(utils):
+    """utils/nms.py + utils/bbox_tools.py on random and hand-made boxes."""
+    rng = np.random.default_rng(7)
+    store = {}
+    for tag, m, span in (("a", 400, 120.0), ("b", 1500, 300.0)):
+        xy = rng.uniform(0, span, size=(m, 2)).astype(np.float32)
+        wh = rng.uniform(4, 60, size=(m, 2)).astype(np.float32)
+        boxes = np.concatenate((xy, xy + wh), axis=1).astype(np.float32)
+        cls = rng.integers(0, 80, size=m).astype(np.float32)
+        boxes_off = (boxes + (cls * np.float32(4096))[:, None]).astype(np.float32)
+        scores = rng.uniform(0, 1, size=m).astype(np.float32)
+        scores[rng.integers(0, m, size=m // 20)] = 0.0          # zero scores are never kept
+        scores[rng.integers(0, m, size=m // 20)] = np.float32(0.5)  # ties -> lower index first
+        store[f"nms_{tag}_boxes"] = boxes_off
+        store[f"nms_{tag}_scores"] = scores
+        for thr in (0.2, 0.5, 0.65):
+            keep = utils.numba_nms(boxes_off, scores, thr)
+            store[f"nms_{tag}_keep_{thr}"] = np.asarray(keep, dtype=np.int32)
+        store[f"iou_{tag}"] = utils.numba_iou(boxes_off[:64], boxes_off[:256])
+    # micro known-answer cases
+    kat_boxes = np.array([[0, 0, 2, 1], [0, 0, 1, 1], [5, 5, 5, 5], [10, 10, 12, 12]], dtype=np.float32)
+    store["kat_boxes"] = kat_boxes
+    store["kat_iou"] = utils.numba_iou(kat_boxes, kat_boxes)
+    store["kat_keep_0.5"] = np.asarray(utils.numba_nms(kat_boxes, np.array([.9, .8, .7, .6], np.float32), 0.5), np.int32)
+    # torch IoU family (float32)
+    xy = rng.uniform(0, 100, size=(200, 2)).astype(np.float32)
+    wh = rng.uniform(1, 50, size=(200, 2)).astype(np.float32)
+    b1 = torch.from_numpy(np.concatenate((xy, xy + wh), axis=1))
+    xy2 = xy + rng.normal(0, 8, size=(200, 2)).astype(np.float32)
+    wh2 = wh * np.exp(rng.normal(0, 0.3, size=(200, 2))).astype(np.float32)
+    b2 = torch.from_numpy(np.concatenate((xy2, xy2 + wh2), axis=1).astype(np.float32))
+    store["tiou_b1"], store["tiou_b2"] = b1.numpy(), b2.numpy()
+    store["tiou_iou"] = utils.gpu_iou(b1[:50], b2).numpy()
+    store["tiou_giou"] = utils.gpu_Giou(b1, b2).numpy()
+    store["tiou_diou"] = utils.gpu_DIoU(b1, b2).numpy()
+    store["tiou_ciou"] = utils.gpu_CIoU(b1, b2).numpy()
+    store["tiou_giou_row"] = utils.gpu_Giou(b1[:1], b2).numpy()
+    store["tiou_diou_row"] = utils.gpu_DIoU(b1[:1], b2).numpy()
+    sc = torch.from_numpy(rng.uniform(0.01, 1, size=200).astype(np.float32))
+    for kind in ("giou", "diou"):
+        store[f"tnms_{kind}"] = np.asarray(utils.gpu_nms(b2, sc, kind, 0.45), dtype=np.int32)
+    store["tnms_scores"] = sc.numpy()
+    store["anchors_64x96"] = utils.GPUAnchor([64, 96])().cpu().numpy()
+    return store
+
+
+def main():
+    utils, trainer = refharness.import_reference()
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, "utils_nms_iou.npz"), **utils_case(utils))
+    fcos_thr = {"compute_metric_cls_threshold": 0.2, "compute_metric_iou_threshold": 0.35, "max_predictions_per_img": 100}
+    cases = [
+        # name, family, dist, img, batch, seed, C, hyp overrides.  Few classes on the small images so that
+        # same-class overlaps (suppression, the count filter) actually occur.
+        ("yolov5_dense_c80_nopp", "yolov5", "dense", 64, 1, 10, 80, {"postprocess_bbox": False}),
+        ("yolov5_dense", "yolov5", "dense", 64, 2, 11, 4, {}),
+        ("yolov5_sparse", "yolov5", "sparse", 128, 2, 12, 6, {}),
+        ("yolov5_crowd", "yolov5", "crowd", 128, 2, 13, 6, {}),
+        ("yolov5_agnostic_off", "yolov5", "dense", 64, 1, 14, 6, {"agnostic": False, "postprocess_bbox": False}),
+        ("yolov5_deploy_thr", "yolov5", "dense", 64, 2, 15, 6,
+         {"compute_metric_conf_threshold": 0.3, "compute_metric_cls_threshold": 0.3, "compute_metric_iou_threshold": 0.2}),
+        ("yolov5_maxdet", "yolov5", "dense", 96, 1, 16, 6, {"max_predictions_per_img": 20, "postprocess_bbox": False}),
+        ("yolov7_dense", "yolov7", "dense", 64, 2, 21, 4, {}),
+        ("yolov7_crowd", "yolov7", "crowd", 128, 1, 22, 6, {}),
+        ("yolox_dense", "yolox", "dense", 64, 2, 31, 4, {}),
+        ("yolox_dense_nopp", "yolox", "dense", 128, 1, 32, 6, {"postprocess_bbox": False}),
+        ("yolov8_dense", "yolov8", "dense", 64, 2, 41, 4, {}),
+        ("yolov8_sparse", "yolov8", "sparse", 64, 1, 42, 6, {}),
+        ("retinanet_dense", "retinanet", "dense", 64, 2, 51, 4, {}),
+        ("retinanet_sparse", "retinanet", "sparse", 96, 1, 52, 6, {}),
+        ("retinanet_exp_dense", "retinanet_exp", "dense", 64, 1, 53, 4, {}),
+        ("fcos_dense", "fcos", "dense", 128, 2, 61, 4, fcos_thr),
+        ("fcos_sparse", "fcos", "sparse", 256, 1, 62, 6, dict(fcos_thr, compute_metric_cls_threshold=0.05)),
+    ]
+    for name, family, dist, img, batch, seed, C, over in cases:
+        store = evaluator_case(trainer, family, dist, img, batch, seed, C, **over)
+        path = os.path.join(OUT, f"{name}.npz")
+        np.savez_compressed(path, **store)
+        print(f"{name:24s} N={store['decoded'].shape[1]:6d} counts={store['counts'].tolist()} "
+              f"{os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,90 @@
+import ast
+import glob
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:  # pragma: no cover
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def golden_names(prefix=""):
+    names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return [n for n in names if n.startswith(prefix) and n != "utils_nms_iou"]
+
+
+def load_golden(name):
+    data = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False))
+    if "meta" in data:
+        data["meta"] = ast.literal_eval(str(data["meta"]))
+    return data
+
+
+def golden_heads(data):
+    """Rebuild the nested head structure saved by oracle/gen_golden.py::_flat_np."""
+    fam = data["meta"]["family"]
+    keys = sorted(k for k in data if k.startswith("head_"))
+    if fam in ("retinanet", "retinanet_exp"):
+        return data["head_0"], data["head_1"]
+    if fam == "fcos":
+        groups = []
+        for gi in range(3):
+            ks = sorted((k for k in keys if k.startswith(f"head_{gi}_")), key=lambda s: int(s.split("_")[-1]))
+            groups.append([data[k] for k in ks])
+        return tuple(groups)
+    ks = sorted(keys, key=lambda s: int(s.split("_")[-1]))
+    return [data[k] for k in ks]
+
+
+def hyp_from_meta(meta):
+    """Oracle-style hyp (thresholds already resolved to the compute_metric_* profile used at generation)."""
+    from oracle import default_hyp
+    return default_hyp(
+        num_class=meta["num_class"], conf_threshold=meta["compute_metric_conf_threshold"],
+        cls_threshold=meta["compute_metric_cls_threshold"], iou_threshold=meta["compute_metric_iou_threshold"],
+        max_predictions_per_img=meta["max_predictions_per_img"], min_prediction_box_wh=meta["min_prediction_box_wh"],
+        mutil_label=meta["mutil_label"], agnostic=meta["agnostic"], postprocess_bbox=meta["postprocess_bbox"],
+        pre_nms_topk=meta["pre_nms_topk"], pre_nms_thresh=meta["pre_nms_thresh"], thresh_with_ctr=meta["thresh_with_ctr"],
+    )
+
+
+def close_rel(a, b, tol=1e-5):
+    """north-star tolerance: |a-b| <= tol * max(|b|, 1)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.abs(a - b) <= tol * np.maximum(np.abs(b), 1.0)
+
+
+def v8_box_scale(meta, reg=16):
+    """Per-candidate magnitude s * (max(gx, gy) + reg) of the operands of the v8 box subtraction."""
+    img = meta["img"]
+    out = []
+    for s in (4, 8, 16, 32):
+        h = img // s
+        n = np.arange(h * h)
+        g = np.maximum(n % h, n // h) + 0.5
+        out.append(s * (g + reg))
+    return np.concatenate(out)

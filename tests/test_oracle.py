@@ -1,0 +1,117 @@
+"""The oracle (oracle/) against the golden vectors produced by the unmodified reference."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import v8_box_scale, close_rel, golden_heads, golden_names, hyp_from_meta, load_golden
+
+
+def _decode(family, heads, meta):
+    C, img = meta["num_class"], meta["img"]
+    if family == "yolov5":
+        return oracle.decode_yolov5(heads, num_class=C)
+    if family == "yolov7":
+        return oracle.decode_yolov7(heads, num_class=C)
+    if family == "yolox":
+        return oracle.decode_yolox(heads, img, num_class=C)
+    if family == "yolov8":
+        return oracle.decode_yolov8(heads, img, num_class=C)
+    if family in ("retinanet", "retinanet_exp"):
+        return oracle.decode_retinanet(heads[0], heads[1], img, img)
+    if family == "fcos":
+        return oracle.decode_fcos(heads[0], heads[1], heads[2], img)
+    raise ValueError(family)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_decode_matches_reference(name):
+    g = load_golden(name)
+    fam = g["meta"]["family"]
+    got = _decode(fam, golden_heads(g), g["meta"])
+    ref = g["decoded"]
+    assert got.shape == ref.shape and got.dtype == np.float32
+    ok = close_rel(got, ref, 1e-5)
+    if fam.startswith("retinanet"):
+        # round_() half-to-even amplifies a 1-ulp exp() difference to 1 px when the pre-round value sits on
+        # x.5; allow those (counted) but nothing else.
+        bad = ~ok
+        assert bad.sum() <= 2 and np.all(np.abs(got[bad] - ref[bad]) <= 1.0)
+    elif fam == "yolov8":
+        # x1 = (g - l) * s cancels: the DFL expectation l is a 16-term float32 dot product whose summation
+        # order torch does not specify, so the bar is 1e-5 relative to the un-cancelled operands s * (g + reg).
+        assert ok[..., 4:].all()
+        assert (np.abs(got[..., :4] - ref[..., :4]) <= 1e-5 * v8_box_scale(g["meta"])[None, :, None]).all()
+    else:
+        assert ok.all(), f"max abs err {np.abs(got - ref).max()}"
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_evaluator_nms_matches_reference(name):
+    g = load_golden(name)
+    fam = g["meta"]["family"]
+    res = oracle.evaluator_nms(fam, g["decoded"], hyp_from_meta(g["meta"]), full_nms=True)
+    assert len(res) == g["counts"].shape[0]
+    for i, r in enumerate(res):
+        cnt = int(g["counts"][i])
+        if cnt < 0:
+            assert r.rows is None
+            continue
+        assert r.rows is not None and r.rows.shape == (cnt, 6)
+        ref = g["rows"][i, :cnt]
+        if fam.startswith("retinanet"):
+            # merged boxes come from a float32 sgemm whose summation order is unspecified
+            np.testing.assert_array_equal(r.rows[:, 4:], ref[:, 4:])
+            assert close_rel(r.rows[:, :4], ref[:, :4], 1e-5).all()
+        else:
+            np.testing.assert_array_equal(r.rows, ref)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_early_stop_equals_full(name):
+    g = load_golden(name)
+    fam = g["meta"]["family"]
+    hyp = hyp_from_meta(g["meta"])
+    full = oracle.evaluator_nms(fam, g["decoded"], hyp, full_nms=True)
+    fast = oracle.evaluator_nms(fam, g["decoded"], hyp, full_nms=False)
+    for a, b in zip(full, fast):
+        assert (a.rows is None) == (b.rows is None)
+        if a.rows is not None:
+            np.testing.assert_array_equal(a.rows, b.rows)
+            np.testing.assert_array_equal(a.cand_index, b.cand_index)
+
+
+def test_utils_nms_and_iou_bit_exact():
+    g = load_golden("utils_nms_iou")
+    for tag in ("a", "b"):
+        boxes, scores = g[f"nms_{tag}_boxes"], g[f"nms_{tag}_scores"]
+        for thr in (0.2, 0.5, 0.65):
+            ref = g[f"nms_{tag}_keep_{thr}"].tolist()
+            assert oracle.numba_nms(boxes, scores, thr) == ref
+            assert oracle.numba_nms(boxes, scores, thr, max_keep=37) == ref[:37]  # prefix stability
+        got = oracle.numba_iou(boxes[:64], boxes[:256])
+        assert got.dtype == np.float64
+        np.testing.assert_array_equal(got, g[f"iou_{tag}"])
+
+
+def test_known_answers():
+    g = load_golden("utils_nms_iou")
+    kat = oracle.numba_iou(g["kat_boxes"], g["kat_boxes"])
+    np.testing.assert_array_equal(kat, g["kat_iou"])  # includes the NaN self-IoU of the degenerate box
+    assert np.isnan(kat[2, 2]) and kat[0, 1] == 0.5
+    assert oracle.numba_nms(g["kat_boxes"], np.array([.9, .8, .7, .6], np.float32), 0.5) == g["kat_keep_0.5"].tolist()
+    # SURVEY.md 8c micro-KATs
+    disjoint = np.array([[0, 0, 1, 1], [10, 0, 11, 1], [20, 0, 21, 1], [30, 0, 31, 1]], np.float32)
+    assert oracle.numba_nms(disjoint, np.array([.5, .9, .9, .1], np.float32), 0.5) == [1, 2, 0, 3]
+    assert oracle.numba_nms(disjoint[:3], np.array([.5, 0, .9], np.float32), 0.5) == [2, 0]
+    assert oracle.numba_nms(np.array([[0, 0, 2, 1], [0, 0, 1, 1]], np.float32), np.array([.9, .8], np.float32), 0.5) == [0]
+
+
+def test_gpu_iou_f32_matches_reference():
+    g = load_golden("utils_nms_iou")
+    got = oracle.gpu_iou_f32(g["tiou_b1"][:50], g["tiou_b2"])
+    assert np.abs(got - g["tiou_iou"]).max() <= 1e-6
+
+
+def test_retinanet_anchors_bit_exact():
+    g = load_golden("utils_nms_iou")
+    np.testing.assert_array_equal(oracle.retinanet_anchors(64, 96), g["anchors_64x96"])

@@ -1,0 +1,171 @@
+"""Seeded synthetic head tensors in the exact layouts the reference models emit.
+
+Used by bench.py, the tests and the golden-fixture generator (there is no network for
+datasets or checkpoints, so every measurement runs on synthetic heads of the named
+shapes -- SURVEY.md section 8d).  Three value distributions:
+
+  dense   every logit ~ N(0, 1): nearly all candidates pass conf=0.001 (M ~ N), random
+          boxes, almost no suppression -- stresses decode + compaction + selection.
+  sparse  objectness ~ N(-9, 1.5), classes ~ N(-2, 1): M ~ 0.5 % of N, the realistic
+          survivor rate; the postprocess_bbox window (1 < M < 3000) is active.
+  crowd   (anchor-grid families) G objects, each written into up to 36 candidates through
+          the inverse decode with small jitter; background objectness -12.  Real
+          suppression depth for the NMS stage.
+
+Layouts (C = num_class):
+  yolov5  list of (b, 3*(5+C), H, W)            strides 8,16,32   utils/layer_tools.py:454-470
+  yolov7  list of (b, 3, H, W, 5+C)             strides 8,16,32   models/normal/yolov7.py:379-405
+  yolox   list of (b, 1, 5+C, H, W)             strides 8,16,32   models/normal/yolox_s.py:129-162
+  yolov8  list of (b, 64+C, H, W)               strides 4,8,16,32 models/normal/yolov8.py:70-81,124
+  retinanet (reg (b,N,4|5), cls (b,N,C))        levels 3..7, 9 anchors/cell
+  fcos    (cls list (b,C,H,W), reg list (b,4,H,W), ctr list (b,1,H,W)) strides 8..128
+"""
+import math
+
+import torch
+
+V5_ANCHORS_PX = [[[10, 13], [16, 30], [33, 23]], [[30, 61], [62, 45], [59, 119]], [[116, 90], [156, 198], [373, 326]]]
+
+FAMILY_STRIDES = {
+    "yolov5": (8, 16, 32),
+    "yolov7": (8, 16, 32),
+    "yolox": (8, 16, 32),
+    "yolov8": (4, 8, 16, 32),
+    "fcos": (8, 16, 32, 64, 128),
+}
+
+
+def level_shapes(family, img_h, img_w):
+    if family in ("retinanet", "retinanet_exp"):
+        return [((img_h - 1) // 2 ** l + 1, (img_w - 1) // 2 ** l + 1) for l in (3, 4, 5, 6, 7)]
+    return [(img_h // s, img_w // s) for s in FAMILY_STRIDES[family]]
+
+
+def num_candidates(family, img_h, img_w):
+    per_cell = {"yolov5": 3, "yolov7": 3, "yolox": 1, "yolov8": 1, "fcos": 1, "retinanet": 9, "retinanet_exp": 9}[family]
+    return per_cell * sum(h * w for h, w in level_shapes(family, img_h, img_w))
+
+
+def _gen(seed, device):
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    return g
+
+
+def _randn(shape, g, device, mean=0.0, std=1.0):
+    return torch.randn(shape, generator=g, device=device, dtype=torch.float32) * std + mean
+
+
+def make_heads(family, batch, img_h=640, img_w=640, num_class=80, dist="dense", seed=1234, device="cpu"):
+    """Returns the head tensors of ``family`` (see module docstring) for ``batch`` images."""
+    g = _gen(seed, device)
+    C = num_class
+    shapes = level_shapes(family, img_h, img_w)
+    if dist == "crowd":
+        if family not in ("yolov5", "yolov7"):
+            raise ValueError("crowd distribution is implemented for the anchor-grid families")
+        heads = _crowd_v5(batch, shapes, C, g, device)
+        if family == "yolov7":
+            heads = [h.view(batch, 3, 5 + C, h.shape[2], h.shape[3]).permute(0, 1, 3, 4, 2).contiguous() for h in heads]
+        return heads
+    if dist not in ("dense", "sparse"):
+        raise ValueError(f"unknown distribution {dist!r}")
+    sparse = dist == "sparse"
+    if family in ("yolov5", "yolov7", "yolox"):
+        na = 1 if family == "yolox" else 3
+        heads = []
+        for h, w in shapes:
+            t = _randn((batch, na, 5 + C, h, w), g, device)
+            if family == "yolox":
+                t[:, :, 2:4] *= 0.5  # keep exp() boxes well below the 4096 class offset
+            if sparse:
+                t[:, :, 4] = t[:, :, 4] * 1.5 - 9.0
+                t[:, :, 5:] = t[:, :, 5:] - 2.0
+            if family == "yolov5":
+                t = t.view(batch, na * (5 + C), h, w)
+            elif family == "yolov7":
+                t = t.permute(0, 1, 3, 4, 2).contiguous()
+            heads.append(t.contiguous())
+        return heads
+    if family == "yolov8":
+        heads = []
+        for h, w in shapes:
+            t = _randn((batch, 64 + C, h, w), g, device)
+            if sparse:
+                t[:, 64:] = t[:, 64:] * 1.5 - 8.0
+            heads.append(t.contiguous())
+        return heads
+    if family in ("retinanet", "retinanet_exp"):
+        n = 9 * sum(h * w for h, w in shapes)
+        reg = _randn((batch, n, 5 if family == "retinanet_exp" else 4), g, device)
+        cls = _randn((batch, n, C), g, device)
+        if sparse:
+            cls = cls * 1.5 - 8.0
+        return reg.contiguous(), cls.contiguous()
+    if family == "fcos":
+        cls_l, reg_l, ctr_l = [], [], []
+        for h, w in shapes:
+            c = _randn((batch, C, h, w), g, device)
+            if sparse:
+                c = c * 1.5 - 5.0
+            cls_l.append(c.contiguous())
+            reg_l.append(_randn((batch, 4, h, w), g, device).abs().contiguous() * 2.0)
+            ctr_l.append(_randn((batch, 1, h, w), g, device).contiguous())
+        return cls_l, reg_l, ctr_l
+    raise ValueError(f"unknown family {family!r}")
+
+
+def _logit(p):
+    p = p.clamp(1e-4, 1 - 1e-4)
+    return torch.log(p) - torch.log1p(-p)
+
+
+def _crowd_v5(batch, shapes, C, g, device, objects_per_image=700):
+    """Objects written through the inverse of the v5 decode (trainer/eval_yolov5.py:203-205)."""
+    strides = FAMILY_STRIDES["yolov5"]
+    img_w = shapes[0][1] * strides[0]
+    img_h = shapes[0][0] * strides[0]
+    heads = []
+    for h, w in shapes:
+        t = _randn((batch, 3, 5 + C, h, w), g, device)
+        t[:, :, 4] = -12.0
+        heads.append(t)
+    anchors = torch.tensor(V5_ANCHORS_PX, dtype=torch.float32, device=device)  # (3, 3, 2)
+    for b in range(batch):
+        G = objects_per_image
+        cx = torch.rand(G, generator=g, device=device) * (img_w - 64) + 32
+        cy = torch.rand(G, generator=g, device=device) * (img_h - 64) + 32
+        bw = torch.exp(torch.rand(G, generator=g, device=device) * math.log(12.0)) * 16.0
+        bh = bw * torch.exp(_randn((G,), g, device, std=0.35))
+        cls_id = torch.randint(0, C, (G,), generator=g, device=device)
+        for lvl, ((h, w), s) in enumerate(zip(shapes, strides)):
+            for a in range(3):
+                aw, ah = anchors[lvl, a, 0], anchors[lvl, a, 1]
+                fit = (bw < 3.6 * aw) & (bh < 3.6 * ah) & (bw > 0.05 * aw) & (bh > 0.05 * ah)
+                for dx in (0, 1):
+                    for dy in (0, 1):
+                        gx = torch.floor(cx / s - 0.5).long() + dx
+                        gy = torch.floor(cy / s - 0.5).long() + dy
+                        ok = fit & (gx >= 0) & (gx < w) & (gy >= 0) & (gy < h)
+                        idx = ok.nonzero().flatten()
+                        if idx.numel() == 0:
+                            continue
+                        n = idx.numel()
+                        jx = cx[idx] + _randn((n,), g, device, std=3.0)
+                        jy = cy[idx] + _randn((n,), g, device, std=3.0)
+                        jw = bw[idx] * torch.exp(_randn((n,), g, device, std=0.08))
+                        jh = bh[idx] * torch.exp(_randn((n,), g, device, std=0.08))
+                        px = ((jx / s - gx[idx].float()) + 0.5) / 2.0
+                        py = ((jy / s - gy[idx].float()) + 0.5) / 2.0
+                        pw = torch.sqrt(jw / aw) / 2.0
+                        ph = torch.sqrt(jh / ah) / 2.0
+                        tgt = heads[lvl][b, a]
+                        yy, xx = gy[idx], gx[idx]
+                        tgt[0, yy, xx] = _logit(px)
+                        tgt[1, yy, xx] = _logit(py)
+                        tgt[2, yy, xx] = _logit(pw)
+                        tgt[3, yy, xx] = _logit(ph)
+                        tgt[4, yy, xx] = _randn((n,), g, device, mean=2.0, std=1.5)
+                        tgt[5:, yy, xx] = _randn((C, n), g, device, mean=-4.0, std=1.0)
+                        tgt[5 + cls_id[idx], yy, xx] = _randn((n,), g, device, mean=2.5, std=1.0)
+    return [t.view(batch, 3 * (5 + C), t.shape[3], t.shape[4]).contiguous() for t in heads]
