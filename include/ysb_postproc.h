@@ -1,0 +1,165 @@
+/*
+ * ysb_postproc.h -- C ABI of the B200-native detection post-processing engine
+ * (libysb_postproc.so, built from yoloseries_b200/csrc by yoloseries_b200/build.py).
+ *
+ * Drop-in boundary for the per-image hot path of yl-jiang/YOLOSeries.  The reference has
+ * no FFI of its own (it is pure Python + numba); the interfaces each entry point stands
+ * behind are the Python call signatures listed in SURVEY.md section 8b:
+ *
+ *   ysb_decode            XEvaluator.do_inference          trainer/eval_yolov5.py:181-209, eval_yolov7.py:123-151,
+ *                                                          eval_yolox.py:123-150, eval_yolov8.py:75-102,
+ *                                                          eval_retinanet.py:59-75 (+22-57,185-200), eval_fcos.py:125-161
+ *   ysb_filter_candidates head of XEvaluator.numba_nms     trainer/eval_yolov5.py:265-286 (and the same block in every
+ *                         (mask, cls*obj, max/argmax)      eval_*.py; operators per family in SURVEY.md 8a-2)
+ *   ysb_select_nms        class offset + utils.numba_nms   trainer/eval_yolov5.py:293-316, utils/nms.py:10-27,
+ *                         + max_det + postprocess_bbox     utils/bbox_tools.py:12-35
+ *   ysb_postprocess       XEvaluator.__call__ minus model  trainer/eval_yolov5.py:30-42
+ *   ysb_nms               utils.numba_nms / utils.gpu_nms  utils/nms.py:10-27 / 30-65
+ *   ysb_pairwise_iou      utils.numba_iou / utils.gpu_iou  utils/bbox_tools.py:12-35 / 164-190
+ *   ysb_elementwise_iou   utils.gpu_Giou/gpu_DIoU/gpu_CIoU utils/bbox_tools.py:193-339
+ *
+ * Conventions: extern "C"; plain pointers and sizes; every pointer named d_* is a DEVICE
+ * pointer owned by the caller; all work is enqueued on the caller's cudaStream_t (passed
+ * as void*) and nothing synchronises the host; no hidden allocation (workspace sizes come
+ * from the *_workspace_bytes queries); return value is a ysb_status (0 = ok, < 0 = error,
+ * never an abort/exception).  There is no CPU fallback: without a CUDA device every
+ * compute entry point returns YSB_ERR_CUDA.
+ */
+#ifndef YSB_POSTPROC_H_
+#define YSB_POSTPROC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YSB_ABI_VERSION 1
+#define YSB_MAX_LEVELS 8
+#define YSB_MAX_ANCHORS 9
+#define YSB_MAX_DET_LIMIT 1024      /* max_det upper bound (kept list lives in shared memory) */
+#define YSB_MAX_CANDIDATES 4194303  /* candidate index must fit 22 bits of the sort key */
+#define YSB_MAX_CLASSES 1024        /* class id must fit 10 bits of the sort key */
+
+typedef enum ysb_status {
+    YSB_OK = 0,
+    YSB_ERR_BAD_ARG = -1,          /* null pointer, negative size, unknown enum value */
+    YSB_ERR_UNSUPPORTED = -2,      /* valid request this build does not implement (e.g. multi_label) */
+    YSB_ERR_WORKSPACE = -3,        /* workspace smaller than *_workspace_bytes() */
+    YSB_ERR_CUDA = -4,             /* a CUDA call failed; see ysb_last_cuda_error() */
+    YSB_ERR_LIMIT = -5             /* N, num_classes or max_det beyond the limits above */
+} ysb_status;
+
+typedef enum ysb_family {
+    YSB_YOLOV5 = 0,        /* heads: L x (b, A*(5+C), H, W)                       trainer/eval_yolov5.py */
+    YSB_YOLOV7 = 1,        /* heads: L x (b, A, H, W, 5+C)                        trainer/eval_yolov7.py */
+    YSB_YOLOX = 2,         /* heads: L x (b, A, 5+C, H, W)                        trainer/eval_yolox.py */
+    YSB_YOLOV8 = 3,        /* heads: L x (b, 4*bins + C, H, W)                    trainer/eval_yolov8.py */
+    YSB_RETINANET = 4,     /* heads: reg (b, N, 4), cls (b, N, C)                 trainer/eval_retinanet.py */
+    YSB_RETINANET_EXP = 5, /* heads: reg (b, N, 5), cls (b, N, C)                 trainer/eval_retinanet_experiment.py */
+    YSB_FCOS = 6           /* heads: L x cls (b,C,H,W), L x reg (b,4,H,W), L x ctr (b,1,H,W)  trainer/eval_fcos.py */
+} ysb_family;
+
+typedef enum ysb_input_kind {
+    YSB_INPUT_RAW_HEADS = 0,   /* raw model outputs; decode is fused into the filter/NMS kernels */
+    YSB_INPUT_DECODED_ROWS = 1 /* the (b, N, C') tensor do_inference returns; heads[0] points at it */
+} ysb_input_kind;
+
+/* IoU flavours.  NUMBA_F64MIX is the live path (utils/bbox_tools.py:12-35: float32 sides/areas,
+ * float64 product/denominator/quotient, no clamp, NaN for 0/0); the others are the float32 torch
+ * routines behind gpu_nms (utils/bbox_tools.py:164-339). */
+typedef enum ysb_iou_kind {
+    YSB_IOU_NUMBA_F64MIX = 0,
+    YSB_IOU_F32 = 1,
+    YSB_GIOU = 2,
+    YSB_DIOU = 3,
+    YSB_CIOU = 4
+} ysb_iou_kind;
+
+typedef enum ysb_cmp { YSB_CMP_GE = 0 /* numba_nms: iou >= thr */, YSB_CMP_GT = 1 /* gpu_nms: iou > thr */ } ysb_cmp;
+
+/* One description of "which heads, which thresholds".  Plain data, passed by pointer, copied by the callee. */
+typedef struct ysb_params {
+    int32_t family;            /* ysb_family */
+    int32_t input_kind;        /* ysb_input_kind */
+    int32_t batch;             /* images in this call */
+    int32_t num_classes;       /* C */
+    int32_t img_h, img_w;      /* network input size (letterboxed pixels) */
+    int32_t num_levels;        /* L (RetinaNet: 5 pyramid levels 3..7) */
+    int32_t level_h[YSB_MAX_LEVELS];
+    int32_t level_w[YSB_MAX_LEVELS];
+    float level_stride[YSB_MAX_LEVELS];
+    int32_t anchors_per_cell;  /* A: 3 (v5/v7), num_anchors (YOLOX), 9 (RetinaNet), 1 otherwise */
+    /* v5/v7: anchor[l][a] = {w/stride, h/stride, 0, 0} as float32 (eval_yolov5.py:192);
+     * RetinaNet: the 9 base anchors {x1,y1,x2,y2} of level l (utils/anchor.py:176-191). */
+    float anchor[YSB_MAX_LEVELS][YSB_MAX_ANCHORS][4];
+    float reg_scale[4];        /* RetinaNet tar_box_scale_factor (eval_retinanet.py:36-39) */
+    int32_t dfl_bins;          /* YOLOv8 'reg' (16) */
+    /* thresholds: float32 because numpy compares float32 arrays with Python floats in float32 */
+    float conf_thr;            /* conf_threshold */
+    float cls_thr;             /* cls_threshold */
+    float pre_nms_thr;         /* FCOS pre_nms_thresh */
+    double iou_thr;            /* iou_threshold, compared in float64 (utils/nms.py:22) */
+    int32_t max_det;           /* max_predictions_per_img */
+    int32_t class_aware;       /* hyp['agnostic'] (sic): add cls*4096 to the boxes before NMS */
+    int32_t multi_label;       /* hyp['mutil_label'] (sic) */
+    int32_t postprocess_bbox;  /* hyp['postprocess_bbox'] */
+    float min_box_wh;          /* min_prediction_box_wh (v7 / FCOS remove_small_boxes) */
+    int32_t pre_nms_topk;      /* FCOS pre_nms_topk */
+    int32_t thresh_with_ctr;   /* FCOS thresh_with_ctr */
+} ysb_params;
+
+int ysb_abi_version(void);
+const char *ysb_status_string(int status);
+/* cudaError_t of the last failing CUDA call made by this library on the calling thread (0 if none). */
+int ysb_last_cuda_error(void);
+
+/* N = candidates per image and the row width C' of the decoded tensor for these params. */
+int ysb_num_candidates(const ysb_params *p, int64_t *n_out, int32_t *row_width_out);
+
+/* do_inference: raw heads -> d_decoded (batch, N, C') float32, reference row layout per family. */
+int ysb_decode(const ysb_params *p, const void *const *d_heads, int num_heads, float *d_decoded, void *stream);
+
+/* Filter + class pick + compaction.  d_keys: (batch, key_capacity) uint64 sort keys
+ *   key = score_bits << 32 | (YSB_MAX_CANDIDATES - cand) << 10 | (1023 - cls)
+ * so that "descending key" == (score desc, candidate asc, class asc), the order numba_nms visits boxes.
+ * d_counts: (batch, 4) int32 = {survivors M, pre-mask passes (FCOS top-k), max score bits, ~min score bits};
+ * zero-filled by this call before the kernels run.  key_capacity >= N (N*C with multi_label). */
+int ysb_filter_candidates(const ysb_params *p, const void *const *d_heads, int num_heads, uint64_t *d_keys,
+                          int64_t key_capacity, int32_t *d_counts, void *stream);
+
+/* Top-k selection + sort + greedy class-aware NMS (early exit at max_det) + postprocess_bbox count filter
+ * (+ RetinaNet merge, + remove_small_boxes) for every image.
+ *   d_dets   (batch, max_det, 6) float32 rows [x1, y1, x2, y2, score, cls], NMS keep order
+ *   d_det_idx(batch, max_det) int32 original candidate index of every row (may be NULL)
+ *   d_det_cnt(batch) int32 number of rows; -1 where the reference returns None */
+int ysb_select_nms(const ysb_params *p, const void *const *d_heads, int num_heads, const uint64_t *d_keys,
+                   int64_t key_capacity, const int32_t *d_counts, float *d_dets, int32_t *d_det_idx,
+                   int32_t *d_det_cnt, void *stream);
+
+/* Whole path = ysb_filter_candidates + ysb_select_nms with the intermediates in d_workspace. */
+int ysb_postprocess_workspace_bytes(const ysb_params *p, size_t *bytes_out);
+int ysb_postprocess(const ysb_params *p, const void *const *d_heads, int num_heads, void *d_workspace,
+                    size_t workspace_bytes, float *d_dets, int32_t *d_det_idx, int32_t *d_det_cnt, void *stream);
+
+/* Greedy NMS over one explicit box/score array (utils.numba_nms / utils.gpu_nms).
+ *   d_boxes (m,4) float32, d_scores (m) float32 >= 0 (zero scores are never kept, utils/nms.py:16)
+ *   max_keep: stop after this many keeps (<= 0: run to exhaustion like the reference)
+ *   d_keep (min(m, max_keep or m)) int32, d_keep_cnt (1) int32 */
+int ysb_nms_workspace_bytes(int64_t m, size_t *bytes_out);
+int ysb_nms(const float *d_boxes, const float *d_scores, int64_t m, double iou_thr, int cmp, int iou_kind,
+            int64_t max_keep, void *d_workspace, size_t workspace_bytes, int32_t *d_keep, int32_t *d_keep_cnt,
+            void *stream);
+
+/* (n,4) x (m,4) -> (n,m).  kind NUMBA_F64MIX writes float64 (numba_iou), F32 writes float32 (gpu_iou). */
+int ysb_pairwise_iou(const float *d_b1, int64_t n, const float *d_b2, int64_t m, int iou_kind, void *d_out,
+                     void *stream);
+/* Row-wise GIoU / DIoU / CIoU with the reference's (1|n,4) x (n,4) broadcasting -> (n) float32. */
+int ysb_elementwise_iou(const float *d_b1, int64_t n1, const float *d_b2, int64_t n2, int iou_kind, float *d_out,
+                        void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YSB_POSTPROC_H_ */

@@ -1,0 +1,122 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference's golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import close_rel, golden_heads, golden_names, hyp_from_meta, load_golden, v8_box_scale
+
+pytestmark = pytest.mark.gpu
+
+
+def _to_dev(x):
+    if isinstance(x, np.ndarray):
+        return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    return type(x)(_to_dev(v) for v in x)
+
+
+def _processor(meta, **over):
+    from yoloseries_b200.engine import PostProcessor
+    from yoloseries_b200.synth import V5_ANCHORS_PX
+    hyp = hyp_from_meta(meta)
+    hyp.update(over)
+    anchors = torch.tensor(V5_ANCHORS_PX) if meta["family"] in ("yolov5", "yolov7") else None
+    return PostProcessor(meta["family"], hyp, anchors=anchors), hyp
+
+
+def _assert_rows_equal(fam, got, ref):
+    assert got.shape == ref.shape
+    if fam.startswith("retinanet"):
+        np.testing.assert_array_equal(got[:, 4:], ref[:, 4:])
+        assert close_rel(got[:, :4], ref[:, :4], 1e-5).all()  # merged boxes: float32 sgemm, order unspecified
+    else:
+        np.testing.assert_array_equal(got, ref)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_decode_vs_reference_golden(name):
+    """ysb_decode == XEvaluator.do_inference of the unmodified reference within 1e-5 relative."""
+    g = load_golden(name)
+    meta = g["meta"]
+    fam = meta["family"]
+    pp, _ = _processor(meta)
+    got = pp.decode(_to_dev(golden_heads(g)), meta["img"], meta["img"]).cpu().numpy()
+    ref = g["decoded"]
+    assert got.shape == ref.shape
+    ok = close_rel(got, ref, 1e-5)
+    if fam.startswith("retinanet"):
+        bad = ~ok  # round_() turns a 1-ulp exp() difference into 1 px when the value sits on x.5
+        assert bad.sum() <= 2 and np.all(np.abs(got[bad] - ref[bad]) <= 1.0)
+    elif fam == "yolov8":
+        assert ok[..., 4:].all()
+        assert (np.abs(got[..., :4] - ref[..., :4]) <= 1e-5 * v8_box_scale(meta)[None, :, None]).all()
+    else:
+        assert ok.all(), f"max abs err {np.abs(got - ref).max()}"
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_decoded_rows_path_vs_reference_golden(name):
+    """Filter + NMS + post-filter on the REFERENCE's decoded tensor == the reference's numba_nms output, bit-exact."""
+    g = load_golden(name)
+    meta = g["meta"]
+    pp, _ = _processor(meta)
+    out = pp.run(_to_dev(g["decoded"]), meta["img"], meta["img"], decoded=True)
+    rows = pp.to_list(out, as_numpy=True)
+    for i, r in enumerate(rows):
+        cnt = int(g["counts"][i])
+        if cnt < 0:
+            assert r is None
+        else:
+            assert r is not None
+            _assert_rows_equal(meta["family"], r, g["rows"][i, :cnt])
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_fused_path_vs_oracle_on_gpu_decode(name):
+    """raw heads -> fused kernels  ==  oracle(numba_nms method) applied to ysb_decode's output, bit-exact,
+    including the original candidate index of every kept row."""
+    g = load_golden(name)
+    meta = g["meta"]
+    fam = meta["family"]
+    pp, hyp = _processor(meta)
+    heads = _to_dev(golden_heads(g))
+    decoded = pp.decode(heads, meta["img"], meta["img"]).cpu().numpy()
+    want = oracle.evaluator_nms(fam, decoded, hyp)
+    out = pp.run(heads, meta["img"], meta["img"])
+    rows, idx = pp.to_list(out, as_numpy=True, with_index=True)
+    for i, w in enumerate(want):
+        if w.rows is None:
+            assert rows[i] is None
+            continue
+        assert rows[i] is not None
+        _assert_rows_equal(fam, rows[i], w.rows)
+        np.testing.assert_array_equal(idx[i], w.cand_index)
+
+
+@pytest.mark.parametrize("family,dist,img,batch,C", [
+    ("yolov5", "dense", 640, 2, 80), ("yolov5", "sparse", 640, 3, 80), ("yolov5", "crowd", 640, 2, 80),
+    ("yolov7", "dense", 640, 2, 80), ("yolox", "dense", 640, 2, 80), ("yolox", "sparse", 640, 2, 80),
+    ("yolov8", "dense", 320, 2, 80), ("retinanet", "dense", 640, 1, 80), ("retinanet", "sparse", 640, 2, 80),
+    ("fcos", "dense", 640, 2, 80), ("fcos", "sparse", 640, 2, 80), ("yolov5", "dense", 1280, 1, 80),
+])
+def test_full_size_fused_vs_oracle(family, dist, img, batch, C):
+    """BASELINE configs at full size: fused CUDA path vs the (early-stop, prefix-stable) oracle on the GPU decode."""
+    from yoloseries_b200 import synth
+    from yoloseries_b200.engine import PostProcessor
+    hyp = oracle.default_hyp(num_class=C)
+    if family == "fcos":
+        hyp.update(cls_threshold=0.2, iou_threshold=0.35, max_predictions_per_img=100)
+    heads = synth.make_heads(family, batch, img, img, C, dist, seed=77, device="cuda")
+    anchors = torch.tensor(synth.V5_ANCHORS_PX) if family in ("yolov5", "yolov7") else None
+    pp = PostProcessor(family, hyp, anchors=anchors)
+    decoded = pp.decode(heads, img, img).cpu().numpy()
+    want = oracle.evaluator_nms(family, decoded, hyp)
+    out = pp.run(heads, img, img)
+    rows, idx = pp.to_list(out, as_numpy=True, with_index=True)
+    for i, w in enumerate(want):
+        if w.rows is None:
+            assert rows[i] is None
+            continue
+        assert rows[i] is not None
+        _assert_rows_equal(family, rows[i], w.rows)
+        np.testing.assert_array_equal(idx[i], w.cand_index)

@@ -1,0 +1,354 @@
+// c_abi.cu -- extern "C" entry points of libysb_postproc.so (see include/ysb_postproc.h).
+//
+// Translates the caller's plain ysb_params + head pointers into the device Plan (geometry + the per-family filter
+// operators of SURVEY.md 8a-2), validates limits, and enqueues the kernels on the caller's stream.  No allocation,
+// no host synchronisation, no exceptions across the boundary.
+#include <cstdio>
+#include <cstring>
+
+#include "ysb_internal.cuh"
+
+namespace ysb {
+cudaError_t launch_filter(const Plan &P, int vec, uint64_t *d_keys, int64_t key_cap, int32_t *d_counts, cudaStream_t stream);
+cudaError_t launch_select_nms(const Plan &P, const uint64_t *d_keys, int64_t key_cap, const int32_t *d_counts,
+                              float *d_dets, int32_t *d_det_idx, int32_t *d_det_cnt, cudaStream_t stream);
+cudaError_t launch_decode(const Plan &P, float *d_out, cudaStream_t stream);
+cudaError_t launch_array_nms(const float *d_boxes, const float *d_scores, int64_t m, double iou_thr, int cmp, int iou_kind,
+                             int64_t max_keep, void *ws, int32_t *d_keep, int32_t *d_keep_cnt, cudaStream_t stream);
+size_t array_nms_workspace_bytes(int64_t m);
+cudaError_t launch_pairwise_iou(const float *b1, int64_t n, const float *b2, int64_t m, int kind, void *out, cudaStream_t stream);
+cudaError_t launch_elementwise_iou(const float *b1, int64_t n1, const float *b2, int64_t n2, int kind, float *out,
+                                   cudaStream_t stream);
+
+static thread_local int g_last_cuda_error = 0;
+
+static int cuda_status(cudaError_t e)
+{
+    if (e == cudaSuccess) return YSB_OK;
+    g_last_cuda_error = static_cast<int>(e);
+    return YSB_ERR_CUDA;
+}
+
+struct Built {
+    Plan plan;
+    int vec;  // 128-bit loads possible for the planes kernel
+    int heads_expected;
+};
+
+static int expected_heads(const ysb_params *p)
+{
+    if (p->input_kind == YSB_INPUT_DECODED_ROWS) return 1;
+    switch (p->family) {
+    case YSB_RETINANET:
+    case YSB_RETINANET_EXP: return 2;
+    case YSB_FCOS: return 3 * p->num_levels;
+    default: return p->num_levels;
+    }
+}
+
+// Fills everything except pointers when d_heads == nullptr (used by the size queries).
+static int build_plan(const ysb_params *p, const void *const *d_heads, int num_heads, Built *out)
+{
+    if (!p || !out) return YSB_ERR_BAD_ARG;
+    if (p->family < YSB_YOLOV5 || p->family > YSB_FCOS) return YSB_ERR_BAD_ARG;
+    if (p->input_kind != YSB_INPUT_RAW_HEADS && p->input_kind != YSB_INPUT_DECODED_ROWS) return YSB_ERR_BAD_ARG;
+    if (p->batch < 0 || p->num_classes <= 0 || p->num_levels <= 0 || p->num_levels > YSB_MAX_LEVELS) return YSB_ERR_BAD_ARG;
+    if (p->anchors_per_cell <= 0 || p->anchors_per_cell > YSB_MAX_ANCHORS) return YSB_ERR_BAD_ARG;
+    if (p->num_classes > YSB_MAX_CLASSES) return YSB_ERR_LIMIT;
+    if (p->max_det <= 0 || p->max_det > YSB_MAX_DET_LIMIT) return YSB_ERR_LIMIT;
+    if (p->multi_label) return YSB_ERR_UNSUPPORTED;
+    const int C = p->num_classes;
+    const int A = p->anchors_per_cell;
+    const int L = p->num_levels;
+    Plan &P = out->plan;
+    std::memset(&P, 0, sizeof(P));
+    P.family = p->family;
+    P.input_kind = p->input_kind;
+    P.batch = p->batch;
+    P.C = C;
+    P.A = A;
+    P.L = L;
+    P.img_h = p->img_h;
+    P.img_w = p->img_w;
+    P.dfl_bins = p->dfl_bins;
+    std::memcpy(P.anchor, p->anchor, sizeof(P.anchor));
+    std::memcpy(P.reg_scale, p->reg_scale, sizeof(P.reg_scale));
+    P.conf_thr = p->conf_thr;
+    P.cls_thr = p->cls_thr;
+    P.pre_thr = p->pre_nms_thr;
+    P.iou_thr = p->iou_thr;
+    P.max_det = p->max_det;
+    P.class_aware = p->class_aware != 0;
+    P.postprocess_bbox = p->postprocess_bbox != 0;
+    P.window_hi = 3000;
+    P.min_box_wh = p->min_box_wh;
+    P.pre_nms_topk = p->pre_nms_topk;
+    P.obj_col = -1;
+
+    int64_t n = 0;
+    for (int l = 0; l < L; ++l) {
+        if (p->level_h[l] <= 0 || p->level_w[l] <= 0) return YSB_ERR_BAD_ARG;
+        LevelDesc &lv = P.lv[l];
+        lv.h = p->level_h[l];
+        lv.w = p->level_w[l];
+        lv.hw = lv.h * lv.w;
+        lv.stride = p->level_stride[l];
+        lv.cand_off = static_cast<int>(n);
+        n += static_cast<int64_t>(A) * lv.hw;
+        if (n > YSB_MAX_CANDIDATES) return YSB_ERR_LIMIT;
+    }
+    P.N = static_cast<int>(n);
+
+    // ---- per-family operators and layouts ---------------------------------------------
+    switch (p->family) {
+    case YSB_YOLOV5:
+    case YSB_YOLOX:
+        P.layout = LAYOUT_PLANES;
+        P.cls_nch = 5 + C; P.cls_ch = 5; P.obj_nch = 5 + C; P.obj_ch = 4; P.obj_src = 0;
+        P.row_w = 5 + C; P.box_col = 0; P.obj_col = 4; P.cls_col = 5; P.box_is_xywh = 1;
+        P.use_obj = 1;
+        P.pre_kind = p->family == YSB_YOLOV5 ? PRE_OBJ : PRE_OBJ_X_MAX;     // eval_yolov5.py:266 / eval_yolox.py:206-207
+        P.post_strict = p->family == YSB_YOLOV5;                             // eval_yolov5.py:285 '>' / eval_yolox.py:227 '>='
+        break;
+    case YSB_YOLOV7:
+        P.layout = LAYOUT_ROWS;
+        P.row_w_in = 5 + C; P.cls_col_in = 5; P.obj_col_in = 4; P.obj_src = 0;
+        P.row_w = 5 + C; P.box_col = 0; P.obj_col = 4; P.cls_col = 5; P.box_is_xywh = 1;
+        P.use_obj = 1; P.pre_kind = PRE_OBJ_X_MAX; P.post_strict = 0;       // eval_yolov7.py:220-221,240
+        P.small_box_filter = 1; P.none_when_empty = 1;                        // eval_yolov7.py:272-280
+        break;
+    case YSB_YOLOV8:
+        if (p->dfl_bins <= 0 || p->dfl_bins > 64) return YSB_ERR_BAD_ARG;
+        P.layout = LAYOUT_PLANES;
+        P.cls_nch = 4 * p->dfl_bins + C; P.cls_ch = 4 * p->dfl_bins; P.obj_src = 0;
+        P.row_w = 4 + C; P.box_col = 0; P.cls_col = 4; P.box_is_xywh = 0;
+        P.use_obj = 0; P.pre_kind = PRE_MAXCLS; P.post_strict = 0;           // eval_yolov8.py:175,195
+        break;
+    case YSB_RETINANET:
+    case YSB_RETINANET_EXP: {
+        const bool ex = p->family == YSB_RETINANET_EXP;
+        P.layout = LAYOUT_ROWS;
+        P.row_w_in = C; P.cls_col_in = 0; P.obj_col_in = -1; P.obj_src = ex ? 1 : 0;
+        P.reg_row_w = ex ? 5 : 4;
+        P.row_w = C + (ex ? 5 : 4); P.cls_col = 0; P.box_col = C; P.obj_col = ex ? C + 4 : -1; P.box_is_xywh = 0;
+        P.use_obj = ex; P.pre_kind = ex ? PRE_OBJ : PRE_NONE; P.post_strict = 1;  // eval_retinanet.py:324 / _experiment.py:320,329
+        P.merge_boxes = 1;                                                         // eval_retinanet.py:349
+        break;
+    }
+    case YSB_FCOS:
+        P.layout = LAYOUT_PLANES;
+        P.cls_nch = C; P.cls_ch = 0; P.obj_nch = 1; P.obj_ch = 0; P.obj_src = 2;
+        P.row_w = 5 + C; P.box_col = 0; P.obj_col = 4; P.cls_col = 5; P.box_is_xywh = 0;
+        P.use_obj = p->thresh_with_ctr != 0; P.pre_kind = PRE_ANY_GT; P.post_strict = 1;  // eval_fcos.py:242-243,252,269
+        P.topk_sqrt = 1; P.window_hi = 301;                                     // eval_fcos.py:272-281,288
+        P.small_box_filter = 1; P.none_when_empty = 1;                          // eval_fcos.py:298-305
+        if (P.pre_nms_topk <= 0) return YSB_ERR_BAD_ARG;
+        break;
+    default: return YSB_ERR_BAD_ARG;
+    }
+    if (p->input_kind == YSB_INPUT_DECODED_ROWS) {
+        // the (b, N, C') tensor: one rows segment, objectness (if any) inside the row
+        P.layout = LAYOUT_ROWS;
+        P.row_w_in = P.row_w; P.cls_col_in = P.cls_col; P.obj_col_in = P.obj_col;
+        if (P.obj_src != 0 && P.use_obj) P.obj_src = 0;
+        if (p->family == YSB_FCOS) P.obj_src = 0;
+    }
+
+    out->heads_expected = expected_heads(p);
+    out->vec = 1;
+    if (P.layout == LAYOUT_PLANES) {
+        bool v4 = true;
+        for (int l = 0; l < L; ++l) v4 = v4 && (P.lv[l].hw % 4 == 0);
+        if (d_heads)
+            for (int i = 0; i < num_heads; ++i) v4 = v4 && ((reinterpret_cast<uintptr_t>(d_heads[i]) & 15u) == 0);
+        out->vec = v4 ? 4 : 1;
+        int units = 0;
+        for (int l = 0; l < L; ++l) {
+            P.lv[l].unit_off = units;
+            units += A * (P.lv[l].hw / out->vec);
+        }
+        P.units_per_img = units;
+    } else if (p->input_kind == YSB_INPUT_DECODED_ROWS) {
+        P.L = 1;
+        P.lv[0].cand_off = 0;
+        P.lv[0].unit_off = 0;
+        P.lv[0].img_rows = P.N;
+        P.units_per_img = (P.N + 127) / 128;
+    } else {
+        int tiles = 0;
+        for (int l = 0; l < L; ++l) {
+            const int rows_l = A * P.lv[l].hw;
+            P.lv[l].unit_off = tiles;
+            P.lv[l].img_rows = (p->family == YSB_YOLOV7) ? rows_l : P.N;
+            tiles += (rows_l + 127) / 128;
+        }
+        P.units_per_img = tiles;
+    }
+
+    if (!d_heads) return YSB_OK;
+    if (num_heads != out->heads_expected) return YSB_ERR_BAD_ARG;
+    for (int i = 0; i < num_heads; ++i)
+        if (!d_heads[i] && P.batch > 0) return YSB_ERR_BAD_ARG;
+    if (p->input_kind == YSB_INPUT_DECODED_ROWS) {
+        P.lv[0].p0 = static_cast<const float *>(d_heads[0]);
+        return YSB_OK;
+    }
+    switch (p->family) {
+    case YSB_RETINANET:
+    case YSB_RETINANET_EXP:
+        for (int l = 0; l < L; ++l) {
+            P.lv[l].p0 = static_cast<const float *>(d_heads[1]) + static_cast<size_t>(P.lv[l].cand_off) * C;
+            P.lv[l].p1 = static_cast<const float *>(d_heads[0]);
+        }
+        break;
+    case YSB_FCOS:
+        for (int l = 0; l < L; ++l) {
+            P.lv[l].p0 = static_cast<const float *>(d_heads[l]);
+            P.lv[l].p1 = static_cast<const float *>(d_heads[L + l]);
+            P.lv[l].p2 = static_cast<const float *>(d_heads[2 * L + l]);
+        }
+        break;
+    default:
+        for (int l = 0; l < L; ++l) P.lv[l].p0 = static_cast<const float *>(d_heads[l]);
+        break;
+    }
+    return YSB_OK;
+}
+
+}  // namespace ysb
+
+using namespace ysb;
+
+extern "C" {
+
+int ysb_abi_version(void) { return YSB_ABI_VERSION; }
+
+const char *ysb_status_string(int status)
+{
+    switch (status) {
+    case YSB_OK: return "ok";
+    case YSB_ERR_BAD_ARG: return "bad argument";
+    case YSB_ERR_UNSUPPORTED: return "unsupported request";
+    case YSB_ERR_WORKSPACE: return "workspace too small";
+    case YSB_ERR_CUDA: return "CUDA error (see ysb_last_cuda_error)";
+    case YSB_ERR_LIMIT: return "size beyond the engine limits";
+    default: return "unknown status";
+    }
+}
+
+int ysb_last_cuda_error(void) { return g_last_cuda_error; }
+
+int ysb_num_candidates(const ysb_params *p, int64_t *n_out, int32_t *row_width_out)
+{
+    Built b;
+    const int st = build_plan(p, nullptr, 0, &b);
+    if (st != YSB_OK) return st;
+    if (n_out) *n_out = b.plan.N;
+    if (row_width_out) *row_width_out = b.plan.row_w;
+    return YSB_OK;
+}
+
+int ysb_decode(const ysb_params *p, const void *const *d_heads, int num_heads, float *d_decoded, void *stream)
+{
+    if (!d_heads || !d_decoded) return YSB_ERR_BAD_ARG;
+    if (p && p->input_kind != YSB_INPUT_RAW_HEADS) return YSB_ERR_BAD_ARG;
+    Built b;
+    const int st = build_plan(p, d_heads, num_heads, &b);
+    if (st != YSB_OK) return st;
+    return cuda_status(launch_decode(b.plan, d_decoded, static_cast<cudaStream_t>(stream)));
+}
+
+int ysb_filter_candidates(const ysb_params *p, const void *const *d_heads, int num_heads, uint64_t *d_keys,
+                          int64_t key_capacity, int32_t *d_counts, void *stream)
+{
+    if (!d_heads || !d_keys || !d_counts) return YSB_ERR_BAD_ARG;
+    Built b;
+    const int st = build_plan(p, d_heads, num_heads, &b);
+    if (st != YSB_OK) return st;
+    if (key_capacity < b.plan.N) return YSB_ERR_WORKSPACE;
+    return cuda_status(launch_filter(b.plan, b.vec, d_keys, key_capacity, d_counts, static_cast<cudaStream_t>(stream)));
+}
+
+int ysb_select_nms(const ysb_params *p, const void *const *d_heads, int num_heads, const uint64_t *d_keys,
+                   int64_t key_capacity, const int32_t *d_counts, float *d_dets, int32_t *d_det_idx,
+                   int32_t *d_det_cnt, void *stream)
+{
+    if (!d_heads || !d_keys || !d_counts || !d_dets || !d_det_cnt) return YSB_ERR_BAD_ARG;
+    Built b;
+    const int st = build_plan(p, d_heads, num_heads, &b);
+    if (st != YSB_OK) return st;
+    return cuda_status(launch_select_nms(b.plan, d_keys, key_capacity, d_counts, d_dets, d_det_idx, d_det_cnt,
+                                         static_cast<cudaStream_t>(stream)));
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+int ysb_postprocess_workspace_bytes(const ysb_params *p, size_t *bytes_out)
+{
+    if (!bytes_out) return YSB_ERR_BAD_ARG;
+    Built b;
+    const int st = build_plan(p, nullptr, 0, &b);
+    if (st != YSB_OK) return st;
+    *bytes_out = align256(sizeof(uint64_t) * static_cast<size_t>(b.plan.N) * b.plan.batch) +
+                 align256(sizeof(int32_t) * 4 * static_cast<size_t>(b.plan.batch)) + 256;
+    return YSB_OK;
+}
+
+int ysb_postprocess(const ysb_params *p, const void *const *d_heads, int num_heads, void *d_workspace,
+                    size_t workspace_bytes, float *d_dets, int32_t *d_det_idx, int32_t *d_det_cnt, void *stream)
+{
+    if (!d_heads || !d_workspace || !d_dets || !d_det_cnt) return YSB_ERR_BAD_ARG;
+    Built b;
+    int st = build_plan(p, d_heads, num_heads, &b);
+    if (st != YSB_OK) return st;
+    size_t need = 0;
+    st = ysb_postprocess_workspace_bytes(p, &need);
+    if (st != YSB_OK) return st;
+    if (workspace_bytes < need) return YSB_ERR_WORKSPACE;
+    uintptr_t base = (reinterpret_cast<uintptr_t>(d_workspace) + 255) & ~static_cast<uintptr_t>(255);
+    uint64_t *d_keys = reinterpret_cast<uint64_t *>(base);
+    int32_t *d_counts = reinterpret_cast<int32_t *>(base + align256(sizeof(uint64_t) * static_cast<size_t>(b.plan.N) * b.plan.batch));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    st = cuda_status(launch_filter(b.plan, b.vec, d_keys, b.plan.N, d_counts, s));
+    if (st != YSB_OK) return st;
+    return cuda_status(launch_select_nms(b.plan, d_keys, b.plan.N, d_counts, d_dets, d_det_idx, d_det_cnt, s));
+}
+
+int ysb_nms_workspace_bytes(int64_t m, size_t *bytes_out)
+{
+    if (!bytes_out || m < 0) return YSB_ERR_BAD_ARG;
+    if (m > YSB_MAX_CANDIDATES) return YSB_ERR_LIMIT;
+    *bytes_out = array_nms_workspace_bytes(m);
+    return YSB_OK;
+}
+
+int ysb_nms(const float *d_boxes, const float *d_scores, int64_t m, double iou_thr, int cmp, int iou_kind,
+            int64_t max_keep, void *d_workspace, size_t workspace_bytes, int32_t *d_keep, int32_t *d_keep_cnt,
+            void *stream)
+{
+    if (m < 0 || !d_keep_cnt || (m > 0 && (!d_boxes || !d_scores || !d_keep || !d_workspace))) return YSB_ERR_BAD_ARG;
+    if (cmp != YSB_CMP_GE && cmp != YSB_CMP_GT) return YSB_ERR_BAD_ARG;
+    if (iou_kind < YSB_IOU_NUMBA_F64MIX || iou_kind > YSB_CIOU) return YSB_ERR_BAD_ARG;
+    if (m > YSB_MAX_CANDIDATES) return YSB_ERR_LIMIT;
+    if (workspace_bytes < array_nms_workspace_bytes(m)) return YSB_ERR_WORKSPACE;
+    return cuda_status(launch_array_nms(d_boxes, d_scores, m, iou_thr, cmp, iou_kind, max_keep, d_workspace, d_keep,
+                                        d_keep_cnt, static_cast<cudaStream_t>(stream)));
+}
+
+int ysb_pairwise_iou(const float *d_b1, int64_t n, const float *d_b2, int64_t m, int iou_kind, void *d_out, void *stream)
+{
+    if (n < 0 || m < 0 || (n > 0 && m > 0 && (!d_b1 || !d_b2 || !d_out))) return YSB_ERR_BAD_ARG;
+    if (iou_kind != YSB_IOU_NUMBA_F64MIX && iou_kind != YSB_IOU_F32) return YSB_ERR_BAD_ARG;
+    return cuda_status(launch_pairwise_iou(d_b1, n, d_b2, m, iou_kind, d_out, static_cast<cudaStream_t>(stream)));
+}
+
+int ysb_elementwise_iou(const float *d_b1, int64_t n1, const float *d_b2, int64_t n2, int iou_kind, float *d_out,
+                        void *stream)
+{
+    if (n1 < 0 || n2 < 0 || (n2 > 0 && (!d_b1 || !d_b2 || !d_out))) return YSB_ERR_BAD_ARG;
+    if (iou_kind != YSB_GIOU && iou_kind != YSB_DIOU && iou_kind != YSB_CIOU) return YSB_ERR_BAD_ARG;
+    if (!(n1 == n2 || n1 == 1)) return YSB_ERR_BAD_ARG;
+    return cuda_status(launch_elementwise_iou(d_b1, n1, d_b2, n2, iou_kind, d_out, static_cast<cudaStream_t>(stream)));
+}
+
+}  // extern "C"

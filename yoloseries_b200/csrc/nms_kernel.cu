@@ -1,0 +1,506 @@
+// nms_kernel.cu -- K2: per-image top-k selection + sort + greedy class-aware NMS + box post-filter.
+//
+// Replaces, per image, trainer/eval_yolov5.py:293-316 (class offset, utils.nms.numba_nms, max_det truncation,
+// postprocess_bbox count filter, row gather) and the same tail in the other evaluators; the NMS itself is
+// utils/nms.py:10-27 with the IoU of utils/bbox_tools.py:12-35.
+//
+// The reference runs the greedy loop over all M survivors (O(K*M), ~14 s per image at M = 25 k) and truncates to
+// max_det afterwards.  Greedy NMS is prefix-stable, so this kernel visits candidates in the reference's order
+// (score desc, candidate asc) and stops at max_det keeps:
+//   1. radix-select (shared-memory histograms over the normalised 64-bit keys) the next <= 4096 best keys,
+//   2. bitonic-sort them in shared memory, decode their boxes (4 channels each) from the head tensors,
+//   3. walk them in chunks of 64: test each against the kept list (parallel), build the 64x64 in-chunk
+//      suppression bitmask (parallel), resolve the chunk with a bitmask sweep (one warp), append the keeps,
+//   4. if fewer than max_det boxes are kept and candidates remain, select the next tranche and continue,
+//   5. postprocess_bbox count filter / RetinaNet merge / remove_small_boxes, ordered write of the rows.
+// One CTA (1024 threads) per image; images of a batch run concurrently on different SMs.
+#include "ysb_internal.cuh"
+
+namespace ysb {
+
+constexpr int kThreads = 1024;
+constexpr int kTrancheCap = 4096;
+constexpr int kMinTranche = 512;
+constexpr int kDigitBits = 11;
+constexpr int kBins = 1 << kDigitBits;
+constexpr int kChunk = 64;
+constexpr int kMaxKeep = YSB_MAX_DET_LIMIT;
+
+struct NmsSmem {
+    uint64_t keys[kTrancheCap];
+    float4 raw[kTrancheCap];
+    uint32_t hist[kBins];
+    OffBox kept_box[kMaxKeep];
+    uint64_t kept_key[kMaxKeep];
+    float4 kept_raw[kMaxKeep];
+    uint8_t kept_flag[kMaxKeep];
+    OffBox chunk_box[kChunk];
+    uint64_t chunk_mask[kChunk];
+    uint8_t chunk_alive[kChunk];
+    uint32_t warp_tmp[kThreads / 32];
+    unsigned long long sel_lo;
+    unsigned long long keep_mask;
+    int n_sel;
+    int sel_digit;
+    int out_count;
+};
+
+// Arguments of the array flavour (utils.numba_nms / utils.gpu_nms on one explicit box array).
+struct ArrayArgs {
+    const float4 *boxes;   // (m) xyxy
+    OffBox *kept_box;      // global workspace (m): the keep list is unbounded here
+    int32_t *keep;         // out: kept indices, visiting order
+    int32_t *keep_cnt;     // out
+    int iou_kind, cmp;
+    float thr32;           // torch compares float32 IoUs against the threshold rounded to float32
+};
+
+template <bool ARRAY>
+__device__ __forceinline__ bool pair_hit(const OffBox &a, const OffBox &b, const IouThr &t, const ArrayArgs &aa)
+{
+    if (!ARRAY) return iou_reaches<false>(a, b, t);
+    if (aa.iou_kind == YSB_IOU_NUMBA_F64MIX) return aa.cmp == YSB_CMP_GT ? iou_reaches<true>(a, b, t) : iou_reaches<false>(a, b, t);
+    const float v = iou_kind_f32(aa.iou_kind, make_float4(a.x1, a.y1, a.x2, a.y2), make_float4(b.x1, b.y1, b.x2, b.y2));
+    return aa.cmp == YSB_CMP_GT ? (v > aa.thr32) : (v >= aa.thr32);
+}
+
+__device__ __forceinline__ uint64_t norm_key(uint64_t key, uint32_t smin)
+{
+    return (static_cast<uint64_t>(static_cast<uint32_t>(key >> 32) - smin) << 32) | (key & 0xffffffffull);
+}
+
+// Block-wide: lower bound `lo` (normalised key space) such that 1 <= #{lo <= nk <= hi_incl} <= kTrancheCap,
+// taking as many keys as fit while stopping the radix descent once kMinTranche keys are covered.
+__device__ uint64_t select_lower_bound(NmsSmem &S, const uint64_t *__restrict__ keys, int M, uint32_t smin,
+                                       uint64_t hi_incl, int nbits)
+{
+    const int tid = threadIdx.x;
+    int sh = nbits > kDigitBits ? nbits - kDigitBits : 0;  // shift of the current digit
+    int width = nbits - sh;                                // bits in the current digit
+    uint64_t prefix = 0;                                   // value of nk >> (sh + width) along the descent path
+    bool have_prefix = false;
+    int acc = 0;                                           // keys already covered above the path
+    for (;;) {
+        for (int i = tid; i < kBins; i += kThreads) S.hist[i] = 0;
+        __syncthreads();
+        const int top = sh + width;
+        for (int i = tid; i < M; i += kThreads) {
+            const uint64_t nk = norm_key(keys[i], smin);
+            if (nk <= hi_incl && (!have_prefix || (top >= 64 ? 0ull : (nk >> top)) == prefix))
+                atomicAdd(&S.hist[(nk >> sh) & ((1u << width) - 1u)], 1u);
+        }
+        __syncthreads();
+        // suffix sums: thread t owns bins 2t, 2t+1
+        const uint32_t h0 = S.hist[2 * tid], h1 = S.hist[2 * tid + 1];
+        uint32_t part = h0 + h1;
+        uint32_t incl = part;  // inclusive suffix over threads >= tid
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_down_sync(0xffffffffu, incl, d);
+            if ((tid & 31) + d < 32) incl += v;
+        }
+        if ((tid & 31) == 0) S.warp_tmp[tid >> 5] = incl;
+        if (tid == 0) S.sel_digit = -1;
+        __syncthreads();
+        uint32_t above = 0;  // sum over warps after mine
+        for (int w = (tid >> 5) + 1; w < kThreads / 32; ++w) above += S.warp_tmp[w];
+        const uint32_t s_hi = incl - part + above;  // S(2t+2): bins strictly above my pair
+        const uint32_t s1 = s_hi + h1;              // S(2t+1)
+        const uint32_t s0 = s1 + h0;                // S(2t)
+        const uint32_t room = static_cast<uint32_t>(kTrancheCap - acc);
+        // d* = smallest digit d with S(d) <= room  <=>  S(d) <= room < S(d-1)
+        if (s1 <= room && s0 > room) S.sel_digit = 2 * tid + 1;
+        else if (s_hi <= room && s1 > room) S.sel_digit = 2 * tid + 2;
+        __syncthreads();
+        const int dstar = S.sel_digit < 0 ? 0 : S.sel_digit;  // -1: even S(0) fits -> whole bucket
+        // covered = acc + S(dstar)
+        if (tid == 0) S.n_sel = 0;
+        __syncthreads();
+        if (dstar == 0) {
+            return have_prefix ? (prefix << top) : 0ull;
+        }
+        // recompute S(dstar) (every thread the same value): owner thread publishes it
+        if (2 * tid + 1 == dstar) S.n_sel = static_cast<int>(s1);
+        if (2 * tid + 2 == dstar) S.n_sel = static_cast<int>(s_hi);
+        __syncthreads();
+        const int covered = acc + S.n_sel;
+        __syncthreads();
+        const uint64_t base = have_prefix ? (prefix << top) : 0ull;
+        if (covered >= kMinTranche || sh == 0) return base | (static_cast<uint64_t>(dstar) << sh);
+        // descend into digit dstar-1
+        prefix = (have_prefix ? (prefix << width) : 0ull) | static_cast<uint64_t>(dstar - 1);
+        have_prefix = true;
+        acc = covered;
+        const int nw = sh < kDigitBits ? sh : kDigitBits;
+        sh -= nw;
+        width = nw;
+    }
+}
+
+__device__ void bitonic_sort_desc(uint64_t *a, int n2)
+{
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (n2 >> 1); t += kThreads) {
+                const int i = ((t / j) * (j << 1)) + (t % j);
+                const int p = i + j;
+                const bool desc = (i & k) == 0;
+                const uint64_t x = a[i], y = a[p];
+                if ((x < y) == desc) { a[i] = y; a[p] = x; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <bool ARRAY>
+__global__ void __launch_bounds__(kThreads, 1)
+k_select_nms(const __grid_constant__ Plan P, const uint64_t *__restrict__ keys_all, int64_t key_cap,
+             const int32_t *__restrict__ counts, float *__restrict__ dets, int32_t *__restrict__ det_idx,
+             int32_t *__restrict__ det_cnt, const ArrayArgs aa)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    NmsSmem &S = *reinterpret_cast<NmsSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int img = blockIdx.x;
+    const int32_t *cnt = counts + img * 4;
+    const int64_t m64 = cnt[0];
+    const int M = static_cast<int>(m64 < key_cap ? m64 : key_cap);
+    if (M <= 0) {
+        if (tid == 0) {
+            if (ARRAY) *aa.keep_cnt = 0;
+            else det_cnt[img] = -1;  // no survivor: the reference appends None
+        }
+        return;
+    }
+    OffBox *const kept_box = ARRAY ? aa.kept_box : S.kept_box;
+    const uint64_t *keys = keys_all + static_cast<int64_t>(img) * key_cap;
+    const uint32_t smax = static_cast<uint32_t>(cnt[2]);
+    const uint32_t smin = ~static_cast<uint32_t>(cnt[3]);
+    const int nbits = 32 + (smax > smin ? 32 - __clz(smax - smin) : 0);
+    const int limit = P.topk_sqrt ? min(M, min(cnt[1], P.pre_nms_topk)) : M;
+    const IouThr thr = make_iou_thr(P.iou_thr);
+    const int max_det = P.max_det;
+    // postprocess_bbox runs only for 1 < M < 3000 (FCOS: <= 300), trainer/eval_yolov5.py:306-307
+    const bool window = !ARRAY && P.postprocess_bbox && M > 1 && M < P.window_hi && M <= kTrancheCap;
+
+    int kept = 0, processed = 0, n_tranche = 0;
+    uint64_t hi_incl = ~0ull;
+    for (;;) {
+        // ---- 1. select the next tranche ------------------------------------------------------------------
+        uint64_t lo = 0;
+        if (M - processed > kTrancheCap) lo = select_lower_bound(S, keys, M, smin, hi_incl, nbits);
+        if (tid == 0) S.n_sel = 0;
+        __syncthreads();
+        for (int i0 = 0; i0 < M; i0 += kThreads) {
+            const int i = i0 + tid;
+            uint64_t key = 0;
+            bool in = false;
+            if (i < M) {
+                key = keys[i];
+                const uint64_t nk = norm_key(key, smin);
+                in = nk >= lo && nk <= hi_incl;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, in);
+            if (bal) {
+                int base = 0;
+                if ((tid & 31) == 0) base = atomicAdd(&S.n_sel, __popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (in) {
+                    const int at = base + __popc(bal & ((1u << (tid & 31)) - 1u));
+                    if (at < kTrancheCap) S.keys[at] = key;
+                }
+            }
+        }
+        __syncthreads();
+        const int n = min(S.n_sel, kTrancheCap);
+        n_tranche = n;
+        // ---- 2. sort descending, decode boxes -------------------------------------------------------------
+        int n2 = 1;
+        while (n2 < n) n2 <<= 1;
+        for (int i = n + tid; i < n2; i += kThreads) S.keys[i] = 0ull;
+        __syncthreads();
+        bitonic_sort_desc(S.keys, n2);
+        const int n_use = min(n, limit - processed);
+        int decoded_upto = 0;  // boxes are decoded 1024 at a time, only as far as the NMS walk gets
+        // ---- 3. greedy NMS over the tranche, 64 candidates at a time ---------------------------------------
+        for (int c0 = 0; c0 < n_use && kept < max_det; c0 += kChunk) {
+            const int cn = min(kChunk, n_use - c0);
+            if (c0 + cn > decoded_upto) {
+                const int i = decoded_upto + tid;
+                if (i < n_use) {
+                    const int cand = static_cast<int>(key_cand(S.keys[i]));
+                    S.raw[i] = ARRAY ? __ldg(aa.boxes + cand) : candidate_xyxy(P, img, cand);
+                }
+                decoded_upto = min(n_use, decoded_upto + kThreads);
+                __syncthreads();
+            }
+            // phase A: 16 threads per candidate test it against the kept list
+            {
+                const int j = tid >> 4, sub = tid & 15;
+                bool sup = false;
+                OffBox ob;
+                bool valid = j < cn;
+                float score = 0.f;
+                if (valid) {
+                    const uint64_t key = S.keys[c0 + j];
+                    score = key_score(key);
+                    const float off = P.class_aware ? __fmul_rn(static_cast<float>(key_cls(key)), 4096.0f) : 0.0f;
+                    ob = make_offbox(S.raw[c0 + j], off);
+                    for (int k = sub; k < kept; k += 16) sup |= pair_hit<ARRAY>(kept_box[k], ob, thr, aa);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, sup);
+                const unsigned half = (tid & 16) ? 0xffff0000u : 0x0000ffffu;
+                if (sub == 0 && j < kChunk) {
+                    // a zero score is never picked by "while sum > 0" (utils/nms.py:16): it is neither kept nor a suppressor
+                    S.chunk_alive[j] = valid && !(bal & half) && score > 0.0f;
+                    if (valid) S.chunk_box[j] = ob;
+                }
+            }
+            __syncthreads();
+            // phase B: in-chunk suppression bitmask, mask[i] bit j (j > i) = IoU(i, j) reaches the threshold
+            {
+                const int i = tid >> 4, sub = tid & 15;
+                uint32_t lo32 = 0, hi32 = 0;
+                if (i < cn && S.chunk_alive[i]) {
+                    const OffBox bi = S.chunk_box[i];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int j = sub * 4 + q;
+                        if (j > i && j < cn && S.chunk_alive[j] && pair_hit<ARRAY>(bi, S.chunk_box[j], thr, aa)) {
+                            if (j < 32) lo32 |= 1u << j; else hi32 |= 1u << (j - 32);
+                        }
+                    }
+                }
+                const unsigned half = (tid & 16) ? 0xffff0000u : 0x0000ffffu;
+                lo32 = __reduce_or_sync(half, lo32);
+                hi32 = __reduce_or_sync(half, hi32);
+                if (sub == 0) S.chunk_mask[i] = (static_cast<uint64_t>(hi32) << 32) | lo32;
+            }
+            __syncthreads();
+            // phase C: resolve the chunk (warp 0)
+            if (tid < 32) {
+                const unsigned a_lo = __ballot_sync(0xffffffffu, S.chunk_alive[tid] != 0);
+                const unsigned a_hi = __ballot_sync(0xffffffffu, S.chunk_alive[tid + 32] != 0);
+                const uint64_t alive = (static_cast<uint64_t>(a_hi) << 32) | a_lo;
+                const bool conflict = (((alive >> tid) & 1ull) && (S.chunk_mask[tid] & alive)) ||
+                                      (((alive >> (tid + 32)) & 1ull) && (S.chunk_mask[tid + 32] & alive));
+                const unsigned any = __ballot_sync(0xffffffffu, conflict);
+                if (tid == 0) {
+                    uint64_t keep = 0;
+                    const int room = max_det - kept;
+                    if (!any) {
+                        keep = alive;
+                    } else {
+                        uint64_t rem = alive;
+                        while (rem) {
+                            const int i = __ffsll(static_cast<long long>(rem)) - 1;
+                            keep |= 1ull << i;
+                            rem &= ~(1ull << i);
+                            rem &= ~S.chunk_mask[i];
+                        }
+                    }
+                    int cntk = __popcll(keep);
+                    while (cntk > room) {  // drop the lowest-priority (highest index) keeps beyond max_det
+                        keep &= ~(1ull << (63 - __clzll(static_cast<long long>(keep))));
+                        --cntk;
+                    }
+                    S.keep_mask = keep;
+                }
+            }
+            __syncthreads();
+            const uint64_t keep = S.keep_mask;
+            if (tid < kChunk && ((keep >> tid) & 1ull)) {
+                const int at = kept + __popcll(keep & ((1ull << tid) - 1ull));
+                kept_box[at] = S.chunk_box[tid];
+                if (ARRAY) {
+                    aa.keep[at] = static_cast<int32_t>(key_cand(S.keys[c0 + tid]));
+                } else {
+                    S.kept_key[at] = S.keys[c0 + tid];
+                    S.kept_raw[at] = S.raw[c0 + tid];
+                }
+            }
+            kept += __popcll(keep);
+            __syncthreads();
+        }
+        if (window) {  // the count filter below needs every survivor's box (single tranche holds them all)
+            for (int i = decoded_upto + tid; i < n_use; i += kThreads)
+                S.raw[i] = candidate_xyxy(P, img, static_cast<int>(key_cand(S.keys[i])));
+            __syncthreads();
+        }
+        processed += n;
+        if (kept >= max_det || processed >= limit || processed >= M) break;
+        hi_incl = lo - 1;  // lo > 0 here: keys remain below it
+    }
+
+    if (ARRAY) {
+        if (tid == 0) *aa.keep_cnt = kept;
+        return;
+    }
+    // ---- 5. postprocess_bbox: a kept box survives iff more than one candidate overlaps it by > thr ----------
+    if (window) {
+        // 1 < M < 3000 <= tranche capacity: the single tranche holds every survivor, boxes decoded for all
+        const int warp = tid >> 5, lane = tid & 31;
+        const int mm = min(n_tranche, limit);
+        for (int r = warp; r < kept; r += kThreads / 32) {
+            const OffBox br = kept_box[r];
+            int c = 0;
+            float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f, ws = 0.f;
+            for (int j = lane; j < mm; j += 32) {
+                const uint64_t key = S.keys[j];
+                const float off = P.class_aware ? __fmul_rn(static_cast<float>(key_cls(key)), 4096.0f) : 0.0f;
+                const float4 rj = S.raw[j];
+                if (iou_reaches<true>(br, make_offbox(rj, off), thr)) {
+                    ++c;
+                    if (P.merge_boxes) {  // trainer/eval_retinanet.py:346-349 (float32 weights, float32 dot)
+                        const float w = key_score(key);
+                        ax = __fadd_rn(ax, __fmul_rn(w, rj.x));
+                        ay = __fadd_rn(ay, __fmul_rn(w, rj.y));
+                        az = __fadd_rn(az, __fmul_rn(w, rj.z));
+                        aw = __fadd_rn(aw, __fmul_rn(w, rj.w));
+                        ws = __fadd_rn(ws, w);
+                    }
+                }
+            }
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (P.merge_boxes) {
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    ax = __fadd_rn(ax, __shfl_xor_sync(0xffffffffu, ax, d));
+                    ay = __fadd_rn(ay, __shfl_xor_sync(0xffffffffu, ay, d));
+                    az = __fadd_rn(az, __shfl_xor_sync(0xffffffffu, az, d));
+                    aw = __fadd_rn(aw, __shfl_xor_sync(0xffffffffu, aw, d));
+                    ws = __fadd_rn(ws, __shfl_xor_sync(0xffffffffu, ws, d));
+                }
+            }
+            if (lane == 0) {
+                S.kept_flag[r] = c > 1;
+                if (P.merge_boxes) {
+                    const float den = __fadd_rn(ws, 1e-16f);
+                    S.kept_raw[r] = make_float4(__fdiv_rn(ax, den), __fdiv_rn(ay, den), __fdiv_rn(az, den), __fdiv_rn(aw, den));
+                }
+            }
+        }
+    } else {
+        for (int r = tid; r < kept; r += kThreads) S.kept_flag[r] = 1;
+    }
+    if (tid == 0) S.out_count = 0;
+    __syncthreads();
+    // ---- ordered write of the surviving rows ---------------------------------------------------------------
+    {
+        const int r = tid;  // kept <= kMaxKeep == kThreads
+        bool pass = false;
+        float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint64_t key = 0;
+        if (r < kept) {
+            box = S.kept_raw[r];
+            key = S.kept_key[r];
+            pass = S.kept_flag[r] != 0;
+            if (pass && P.small_box_filter)  // remove_small_boxes, trainer/eval_yolov7.py:203-213
+                pass = (__fsub_rn(box.z, box.x) > P.min_box_wh) && (__fsub_rn(box.w, box.y) > P.min_box_wh);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+        if ((tid & 31) == 0) S.warp_tmp[tid >> 5] = __popc(bal);
+        __syncthreads();
+        int before = 0;
+        for (int w = 0; w < (tid >> 5); ++w) before += S.warp_tmp[w];
+        if (pass) {
+            const int at = before + __popc(bal & ((1u << (tid & 31)) - 1u));
+            float *row = dets + (static_cast<size_t>(img) * max_det + at) * 6;
+            const float sc = key_score(key);
+            row[0] = box.x; row[1] = box.y; row[2] = box.z; row[3] = box.w;
+            row[4] = P.topk_sqrt ? sqrtf(sc) : sc;  // FCOS: x[:, 4] = sqrt(x[:, 4]) (trainer/eval_fcos.py:281)
+            row[5] = static_cast<float>(key_cls(key));
+            if (det_idx) det_idx[static_cast<size_t>(img) * max_det + at] = static_cast<int32_t>(key_cand(key));
+        }
+        if (tid == kThreads - 1) {
+            const int total = before + __popc(bal);
+            det_cnt[img] = (total == 0 && P.none_when_empty) ? -1 : total;
+        }
+    }
+}
+
+cudaError_t launch_select_nms(const Plan &P, const uint64_t *d_keys, int64_t key_cap, const int32_t *d_counts,
+                              float *d_dets, int32_t *d_det_idx, int32_t *d_det_cnt, cudaStream_t stream)
+{
+    if (P.batch == 0) return cudaSuccess;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_select_nms<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(sizeof(NmsSmem)));
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    ArrayArgs aa{};
+    k_select_nms<false><<<P.batch, kThreads, sizeof(NmsSmem), stream>>>(P, d_keys, key_cap, d_counts, d_dets, d_det_idx,
+                                                                         d_det_cnt, aa);
+    return cudaGetLastError();
+}
+
+// ---- array flavour: utils.numba_nms / utils.gpu_nms over one explicit (m,4)/(m) pair ---------------------------
+// zero scores are never kept (utils/nms.py:16 "while score.sum() > 0"); keys carry the array index.
+__global__ void k_array_keys(const float *__restrict__ scores, int m, uint64_t *__restrict__ keys, int32_t *__restrict__ counts)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = i < m && scores[i] > 0.0f;
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (!bal) return;
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t sb = ok ? __float_as_uint(scores[i]) : 0u;
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, sb);
+    const uint32_t wmin = __reduce_max_sync(0xffffffffu, ok ? ~sb : 0u);
+    int base = 0;
+    if (lane == 0) {
+        base = atomicAdd(counts, __popc(bal));
+        atomicMax(reinterpret_cast<unsigned int *>(counts + 2), wmax);
+        atomicMax(reinterpret_cast<unsigned int *>(counts + 3), wmin);
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (ok) keys[base + __popc(bal & ((1u << lane) - 1u))] = pack_key(scores[i], static_cast<uint32_t>(i), 0u);
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+size_t array_nms_workspace_bytes(int64_t m)
+{
+    const size_t mm = static_cast<size_t>(m > 0 ? m : 1);
+    return align256(sizeof(uint64_t) * mm) + align256(sizeof(OffBox) * mm) + align256(sizeof(int32_t) * 4) + 256;
+}
+
+cudaError_t launch_array_nms(const float *d_boxes, const float *d_scores, int64_t m, double iou_thr, int cmp, int iou_kind,
+                             int64_t max_keep, void *ws, int32_t *d_keep, int32_t *d_keep_cnt, cudaStream_t stream)
+{
+    if (m == 0) return cudaMemsetAsync(d_keep_cnt, 0, sizeof(int32_t), stream);
+    const size_t mm = static_cast<size_t>(m);
+    uintptr_t base = (reinterpret_cast<uintptr_t>(ws) + 255) & ~static_cast<uintptr_t>(255);
+    uint64_t *keys = reinterpret_cast<uint64_t *>(base);
+    OffBox *kept = reinterpret_cast<OffBox *>(base + align256(sizeof(uint64_t) * mm));
+    int32_t *counts = reinterpret_cast<int32_t *>(base + align256(sizeof(uint64_t) * mm) + align256(sizeof(OffBox) * mm));
+    cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int32_t) * 4, stream);
+    if (e != cudaSuccess) return e;
+    k_array_keys<<<static_cast<unsigned>((m + 255) / 256), 256, 0, stream>>>(d_scores, static_cast<int>(m), keys, counts);
+    static bool attr_set = false;
+    if (!attr_set) {
+        e = cudaFuncSetAttribute(k_select_nms<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(NmsSmem)));
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    Plan P;
+    memset(&P, 0, sizeof(P));
+    P.batch = 1;
+    P.N = static_cast<int>(m);
+    P.iou_thr = iou_thr;
+    P.max_det = static_cast<int>((max_keep > 0 && max_keep < m) ? max_keep : m);
+    ArrayArgs aa;
+    aa.boxes = reinterpret_cast<const float4 *>(d_boxes);
+    aa.kept_box = kept;
+    aa.keep = d_keep;
+    aa.keep_cnt = d_keep_cnt;
+    aa.iou_kind = iou_kind;
+    aa.cmp = cmp;
+    aa.thr32 = static_cast<float>(iou_thr);
+    k_select_nms<true><<<1, kThreads, sizeof(NmsSmem), stream>>>(P, keys, m, counts, nullptr, nullptr, nullptr, aa);
+    return cudaGetLastError();
+}
+
+}  // namespace ysb

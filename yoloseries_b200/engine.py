@@ -1,0 +1,250 @@
+"""Host-side engine: turns (family, hyp, head tensors) into ysb_params + device buffers and calls the C ABI.
+
+PyTorch is plumbing here (device memory, current stream, pinned host buffers); all compute happens in
+libysb_postproc.so.  Nothing in this module computes on the CPU and nothing falls back to torch ops.
+"""
+import ctypes
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import YsbParams
+
+# strides fixed by the reference evaluators (self.ds_scales), trainer/eval_yolov5.py:21, eval_yolov7.py, eval_fcos.py:18
+_FIXED_STRIDES = {"yolov5": (8, 16, 32), "yolov7": (8, 16, 32), "fcos": (8, 16, 32, 64, 128)}
+
+
+def retinanet_base_anchors(size):
+    """The 9 base anchors of one pyramid level, float32, ratio-major (utils/anchor.py:176-191).
+
+    Every step is a single correctly-rounded float32 operation (mul, div, sqrt, sub), so this numpy restatement is
+    bit-identical to the torch code of the reference; the device kernel adds the per-cell shift analytically.
+    """
+    f = np.float32
+    scales = np.array([1, 2 ** (1 / 3), 2 ** (2 / 3)], dtype=f)
+    ratios = np.array([0.5, 1, 2], dtype=f)
+    side = f(size) * np.tile(scales, 3)
+    areas = side * side
+    rr = np.repeat(ratios, 3)
+    w = np.sqrt(areas / rr)
+    h = w * rr
+    out = np.zeros((9, 4), dtype=f)
+    out[:, 0] = f(0) - w / f(2)
+    out[:, 1] = f(0) - h / f(2)
+    out[:, 2] = w - w / f(2)
+    out[:, 3] = h - h / f(2)
+    return out
+
+
+def flatten_heads(family, heads):
+    """Head tensors in the order the C ABI expects (include/ysb_postproc.h, enum ysb_family)."""
+    if family in ("retinanet", "retinanet_exp"):
+        reg, cls = heads
+        return [reg, cls]
+    if family == "fcos":
+        cls_l, reg_l, ctr_l = heads
+        return list(cls_l) + list(reg_l) + list(ctr_l)
+    if isinstance(heads, (dict, OrderedDict)):
+        return list(heads.values())
+    return list(heads)
+
+
+def _level_shapes(family, flat, num_class):
+    if family in ("yolov5", "yolox", "yolov8"):
+        return [(t.shape[-2], t.shape[-1]) for t in flat]
+    if family == "yolov7":
+        return [(t.shape[2], t.shape[3]) for t in flat]
+    if family == "fcos":
+        n = len(flat) // 3
+        return [(t.shape[2], t.shape[3]) for t in flat[:n]]
+    raise ValueError(family)
+
+
+def make_params(family, hyp, batch, img_h, img_w, level_shapes=None, anchors=None, input_kind=_lib.INPUT_RAW_HEADS,
+                compute_metric=False, num_anchors=None):
+    """Build ``ysb_params`` from the reference's flat ``hyp`` dict (SURVEY.md section 5 lists the keys)."""
+    p = YsbParams()
+    p.family = _lib.FAMILY_IDS[family]
+    p.input_kind = input_kind
+    p.batch = int(batch)
+    p.num_classes = int(hyp["num_class"])
+    p.img_h, p.img_w = int(img_h), int(img_w)
+    pre = "compute_metric_" if compute_metric else ""
+    p.iou_thr = float(hyp[pre + "iou_threshold"])
+    p.cls_thr = float(hyp[pre + "cls_threshold"])
+    p.conf_thr = float(hyp.get(pre + "conf_threshold", 0.0))
+    p.pre_nms_thr = float(hyp.get("pre_nms_thresh", 0.0))
+    p.max_det = int(hyp["max_predictions_per_img"])
+    p.class_aware = int(bool(hyp["agnostic"]))
+    p.multi_label = int(bool(hyp["mutil_label"]))
+    p.postprocess_bbox = int(bool(hyp["postprocess_bbox"]))
+    p.min_box_wh = float(hyp.get("min_prediction_box_wh", 0))
+    p.pre_nms_topk = int(hyp.get("pre_nms_topk", 1000))
+    p.thresh_with_ctr = int(bool(hyp.get("thresh_with_ctr", True)))
+    p.dfl_bins = int(hyp.get("reg", 16))
+    scale = hyp.get("tar_box_scale_factor", [0.1, 0.1, 0.2, 0.2])
+    for i in range(4):
+        p.reg_scale[i] = float(scale[i])
+    if family in ("retinanet", "retinanet_exp"):
+        levels = (3, 4, 5, 6, 7)
+        p.num_levels = len(levels)
+        p.anchors_per_cell = 9
+        for i, lvl in enumerate(levels):
+            p.level_h[i] = (img_h - 1) // 2 ** lvl + 1
+            p.level_w[i] = (img_w - 1) // 2 ** lvl + 1
+            p.level_stride[i] = float(2 ** lvl)
+            base = retinanet_base_anchors(2 ** (lvl + 2))
+            for a in range(9):
+                for c in range(4):
+                    p.anchor[i][a][c] = float(base[a, c])
+        return p
+    if level_shapes is None:
+        raise ValueError("level_shapes is required for grid families")
+    p.num_levels = len(level_shapes)
+    for i, (h, w) in enumerate(level_shapes):
+        p.level_h[i], p.level_w[i] = int(h), int(w)
+        if family in _FIXED_STRIDES:
+            p.level_stride[i] = float(_FIXED_STRIDES[family][i]) if family != "fcos" else float(img_h / h)
+        else:
+            p.level_stride[i] = float(img_h / h)  # eval_yolox.py:144, eval_yolov8.py:91
+    if family in ("yolov5", "yolov7"):
+        if anchors is None:
+            raise ValueError("anchors (L, A, 2) are required for yolov5 / yolov7")
+        anc = torch.as_tensor(anchors).detach().cpu()
+        p.anchors_per_cell = int(anc.shape[1])
+        for i in range(anc.shape[0]):
+            # (self.anchors[i] / self.ds_scales[i]).type_as(inputs): true divide, then float32 (eval_yolov5.py:192)
+            stage = (anc[i] / _FIXED_STRIDES[family][i]).to(torch.float32)
+            for a in range(anc.shape[1]):
+                p.anchor[i][a][0] = float(stage[a, 0])
+                p.anchor[i][a][1] = float(stage[a, 1])
+    elif family == "yolox":
+        p.anchors_per_cell = int(num_anchors or hyp.get("num_anchors", 1))
+    else:
+        p.anchors_per_cell = 1
+    return p
+
+
+class DetectionBuffers:
+    """Per-call device outputs: rows (b, max_det, 6), candidate indices (b, max_det), counts (b)."""
+
+    def __init__(self, batch, max_det, device):
+        self.dets = torch.empty((batch, max_det, 6), dtype=torch.float32, device=device)
+        self.det_idx = torch.empty((batch, max_det), dtype=torch.int32, device=device)
+        self.det_cnt = torch.empty((batch,), dtype=torch.int32, device=device)
+
+
+class PostProcessor:
+    """decode -> filter -> top-k -> class-aware NMS -> post-filter for one family / one head geometry.
+
+    Buffers are allocated once per (batch, geometry) and reused; every call enqueues on torch's current stream.
+    """
+
+    def __init__(self, family, hyp, anchors=None, compute_metric=False):
+        self.family = family
+        self.hyp = dict(hyp)
+        self.anchors = anchors
+        self.compute_metric = compute_metric
+        self._lib = _lib.load()
+        self._cache = {}
+
+    # ---- plumbing ------------------------------------------------------------------------------------------
+    def _prepare(self, flat, batch, img_h, img_w, input_kind):
+        dev = flat[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("yoloseries_b200 runs on CUDA devices only (no CPU fallback); got " + str(dev))
+        for t in flat:
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("head tensors must be contiguous float32")
+        shapes = None
+        if input_kind == _lib.INPUT_RAW_HEADS and self.family not in ("retinanet", "retinanet_exp"):
+            shapes = _level_shapes(self.family, flat, self.hyp["num_class"])
+        elif self.family not in ("retinanet", "retinanet_exp"):
+            strides = _FIXED_STRIDES.get(self.family) or ((4, 8, 16, 32) if self.family == "yolov8" else (8, 16, 32))
+            shapes = [(img_h // s, img_w // s) for s in strides]
+        na = flat[0].shape[1] if (self.family == "yolox" and input_kind == _lib.INPUT_RAW_HEADS) else None
+        key = (batch, img_h, img_w, input_kind, tuple(shapes or ()), dev.index, na)
+        ent = self._cache.get(key)
+        if ent is None:
+            params = make_params(self.family, self.hyp, batch, img_h, img_w, shapes, self.anchors, input_kind,
+                                 self.compute_metric, na)
+            n = ctypes.c_int64()
+            rw = ctypes.c_int32()
+            _lib.check(self._lib.ysb_num_candidates(ctypes.byref(params), ctypes.byref(n), ctypes.byref(rw)),
+                       "ysb_num_candidates")
+            ws = ctypes.c_size_t()
+            _lib.check(self._lib.ysb_postprocess_workspace_bytes(ctypes.byref(params), ctypes.byref(ws)),
+                       "ysb_postprocess_workspace_bytes")
+            ent = dict(params=params, N=n.value, row_w=rw.value,
+                       workspace=torch.empty(max(ws.value, 1), dtype=torch.uint8, device=dev),
+                       out=DetectionBuffers(batch, params.max_det, dev))
+            self._cache[key] = ent
+        return ent
+
+    @staticmethod
+    def _stream():
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    # ---- public ops ----------------------------------------------------------------------------------------
+    def decode(self, heads, img_h, img_w):
+        """do_inference: raw heads -> (b, N, C') float32 on the heads' device."""
+        flat = flatten_heads(self.family, heads)
+        batch = flat[0].shape[0]
+        ent = self._prepare(flat, batch, img_h, img_w, _lib.INPUT_RAW_HEADS)
+        out = torch.empty((batch, ent["N"], ent["row_w"]), dtype=torch.float32, device=flat[0].device)
+        ptrs = _lib.head_pointer_array(flat)
+        _lib.check(self._lib.ysb_decode(ctypes.byref(ent["params"]), ptrs, len(flat), out.data_ptr(), self._stream()),
+                   "ysb_decode")
+        return out
+
+    def run(self, heads, img_h, img_w, decoded=False):
+        """Whole path on the device.  Returns DetectionBuffers (views into reused storage)."""
+        flat = [heads] if decoded else flatten_heads(self.family, heads)
+        batch = flat[0].shape[0]
+        kind = _lib.INPUT_DECODED_ROWS if decoded else _lib.INPUT_RAW_HEADS
+        ent = self._prepare(flat, batch, img_h, img_w, kind)
+        if decoded and (flat[0].shape[1] != ent["N"] or flat[0].shape[2] != ent["row_w"]):
+            raise ValueError(f"decoded tensor must be (b, {ent['N']}, {ent['row_w']}), got {tuple(flat[0].shape)}")
+        out = ent["out"]
+        ptrs = _lib.head_pointer_array(flat)
+        ws = ent["workspace"]
+        _lib.check(self._lib.ysb_postprocess(ctypes.byref(ent["params"]), ptrs, len(flat), ws.data_ptr(), ws.numel(),
+                                             out.dets.data_ptr(), out.det_idx.data_ptr(), out.det_cnt.data_ptr(),
+                                             self._stream()), "ysb_postprocess")
+        return out
+
+    def filter_only(self, heads, img_h, img_w, decoded=False):
+        """K1 alone: returns (keys (b, N) uint64 as int64 tensor, counts (b, 4) int32)."""
+        flat = [heads] if decoded else flatten_heads(self.family, heads)
+        batch = flat[0].shape[0]
+        kind = _lib.INPUT_DECODED_ROWS if decoded else _lib.INPUT_RAW_HEADS
+        ent = self._prepare(flat, batch, img_h, img_w, kind)
+        dev = flat[0].device
+        keys = torch.empty((batch, ent["N"]), dtype=torch.int64, device=dev)
+        counts = torch.empty((batch, 4), dtype=torch.int32, device=dev)
+        ptrs = _lib.head_pointer_array(flat)
+        _lib.check(self._lib.ysb_filter_candidates(ctypes.byref(ent["params"]), ptrs, len(flat), keys.data_ptr(),
+                                                   ent["N"], counts.data_ptr(), self._stream()),
+                   "ysb_filter_candidates")
+        return keys, counts
+
+    @staticmethod
+    def to_list(out, as_numpy=False, with_index=False):
+        """DetectionBuffers -> the reference's output contract: list of CPU float32 (K, 6) tensors or None."""
+        cnt = out.det_cnt.cpu()
+        kmax = int(cnt.max().item()) if cnt.numel() else 0
+        rows = out.dets[:, : max(kmax, 1)].cpu()
+        idx = out.det_idx[:, : max(kmax, 1)].cpu() if with_index else None
+        res, ids = [], []
+        for i, c in enumerate(cnt.tolist()):
+            if c < 0:
+                res.append(None)
+                ids.append(None)
+                continue
+            r = rows[i, :c].clone()
+            res.append(r.numpy() if as_numpy else r)
+            if with_index:
+                ids.append(idx[i, :c].clone().numpy())
+        return (res, ids) if with_index else res
