@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- post-processing throughput (images/s) of the B200 engine on BASELINE.json's headline config.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K ...  (the reference's CPU algorithm on the host cores)
+
+A "step" is one pass of the hot path (filter/compaction kernel + select/sort/NMS kernel) over one batch of
+synthetic YOLOv5s 640x640 head tensors (3 levels, 25,200 candidates/image, 80 classes, conf=cls=0.001, iou=0.65,
+max_det=300, class-aware).  Every rank owns `--batch` images (weak scaling: BASELINE config[1]'s 64 images per
+GPU); at N > 1 the step ends with the all-gather of the padded kept detections (the only collective on the path).
+
+Output: ONE JSON line on rank 0 (see the keys in main()).
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "post-proc images/s (YOLOv5s 640^2, conf=0.001)"
+UNIT = "images/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="images per rank per step")
+    ap.add_argument("--family", default="yolov5")
+    ap.add_argument("--img", type=int, default=640)
+    ap.add_argument("--dist", default="dense", choices=["dense", "sparse", "crowd"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-images", type=int, default=2, help="images in the bounded CPU-baseline sample")
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"{args.family} {args.img}x{args.img} decode+filter+top-k+class-aware NMS, "
+                    f"{args.batch} images/GPU/step, 80 classes, conf=cls=0.001, iou=0.65, max_det=300, "
+                    f"postprocess_bbox=true, distribution={args.dist}",
+        "images_per_gpu_per_step": args.batch,
+        "global_batch": args.batch * world,
+        "distribution": args.dist,
+        "parallelism": f"image-sharded x{world}" + (", all-gather of kept detections" if world > 1 else ""),
+        "l2": "inputs per step (548 MB at 64 images) exceed the 126 MB L2; streamed once per step",
+    }
+
+
+def bench_hyp():
+    import oracle
+    return oracle.default_hyp(num_class=80)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks: sampled with NVML while the timed workload is running
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._armed = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)),
+        }
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            if self._armed.is_set():
+                try:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    r = get_reasons(self.h)
+                    for k, bit in names.items():
+                        if r & bit:
+                            self.reasons.add(k)
+                except Exception:
+                    pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+
+    def arm(self, on):
+        (self._armed.set if on else self._armed.clear)()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=1)
+        return {
+            "sm_mhz": statistics.median(self.samples) if self.samples else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU legs (oracle = plain C/numpy restatement of the reference's algorithm; the only place bench.py touches it)
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_heads(n_images, args, seed=4321):
+    from yoloseries_b200 import synth
+    return [h.numpy() for h in synth.make_heads(args.family, n_images, args.img, args.img, 80, args.dist, seed, "cpu")]
+
+
+def cpu_images_per_second(heads_np, threads):
+    """Time the reference's CPU algorithm (decode -> filter -> FULL greedy NMS loop, no early stop -> post-filter)
+    on the given synthetic images of the bench workload using `threads` host threads (one image per task)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    import oracle
+
+    hyp = bench_hyp()
+    n_images = heads_np[0].shape[0]
+
+    def one(i):
+        dec = oracle.decode_yolov5([h[i:i + 1] for h in heads_np])
+        return oracle.evaluator_nms("yolov5", dec, hyp, full_nms=True)
+
+    t0 = time.perf_counter()
+    if threads <= 1:
+        for i in range(n_images):
+            one(i)
+    else:
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            list(ex.map(one, range(n_images)))
+    dt = time.perf_counter() - t0
+    return n_images / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    if args.family != "yolov5":
+        print(json.dumps({"impl": "reference", "unavailable": "reference arm implemented for the yolov5 headline config"}))
+        return
+    import oracle
+    oracle.load_library()
+    threads = os.cpu_count() or 1
+    budget_s = 240.0
+    warm = min(args.warmup, 1)
+    t_first = None
+    heads_np = cpu_heads(threads, args)  # generated once; every step processes the same `threads` images
+    for _ in range(warm):
+        _, t_first = cpu_images_per_second(heads_np, threads)
+    done, total_t = 0, 0.0
+    for k in range(args.steps):
+        _, dt = cpu_images_per_second(heads_np, threads)
+        done += 1
+        total_t += dt
+        if total_t + (t_first or 0.0) > budget_s:
+            break
+    value = threads * done / total_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": done,
+        "steps_requested": args.steps, "warmup": warm, "ms_per_step": 1e3 * total_t / done, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (+f64 IoU)", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{threads} images per step, one per host thread, full greedy NMS loop as "
+                                   "utils/nms.py runs it (no early stop); C/numpy port of the reference algorithm "
+                                   "(the reference itself is Python+numba and cannot travel to this box)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+
+    from yoloseries_b200 import _lib, synth
+    from yoloseries_b200.engine import PostProcessor, flatten_heads
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    hyp = bench_hyp()
+    heads = synth.make_heads(args.family, args.batch, args.img, args.img, 80, args.dist, 1234 + rank, dev)
+    anchors = torch.tensor(synth.V5_ANCHORS_PX) if args.family in ("yolov5", "yolov7") else None
+    pp = PostProcessor(args.family, hyp, anchors=anchors)
+    flat = flatten_heads(args.family, heads)
+    ent = pp._prepare(flat, args.batch, args.img, args.img, _lib.INPUT_RAW_HEADS)
+    lib = _lib.load()
+    params, N, out = ent["params"], ent["N"], ent["out"]
+    keys = torch.empty((args.batch, N), dtype=torch.int64, device=dev)
+    counts = torch.zeros((args.batch, 4), dtype=torch.int32, device=dev)
+    ptrs = _lib.head_pointer_array(flat)
+    max_det = params.max_det
+    # One flat buffer per rank = [rows (b, max_det, 6) f32 | counts (b) i32]: the NMS kernel writes straight into it
+    # and, at N > 1, it is the (fixed-stride, no size pre-exchange) send buffer of the all-gather.
+    n_row_f = args.batch * max_det * 6
+    flat_send = torch.zeros(n_row_f + args.batch, dtype=torch.float32, device=dev)
+    dets_dense = flat_send[:n_row_f].view(args.batch, max_det, 6)
+    cnt_view = flat_send[n_row_f:].view(torch.int32)
+    gathered = torch.empty((world, n_row_f + args.batch), dtype=torch.float32, device=dev) if world > 1 else None
+    stream = torch.cuda.current_stream()
+    sp = ctypes.c_void_p(stream.cuda_stream)
+
+    def launch(head_ptrs):
+        _lib.check(lib.ysb_filter_candidates(ctypes.byref(params), head_ptrs, len(flat), keys.data_ptr(), N,
+                                             counts.data_ptr(), sp), "ysb_filter_candidates")
+
+    def launch_nms(head_ptrs):
+        _lib.check(lib.ysb_select_nms(ctypes.byref(params), head_ptrs, len(flat), keys.data_ptr(), N,
+                                      counts.data_ptr(), dets_dense.data_ptr(), out.det_idx.data_ptr(),
+                                      cnt_view.data_ptr(), sp), "ysb_select_nms")
+
+    def step(ev=None):
+        if ev:
+            ev[0].record(stream)
+        launch(ptrs)
+        if ev:
+            ev[1].record(stream)
+        launch_nms(ptrs)
+        if ev:
+            ev[2].record(stream)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), flat_send)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    # ---- timed region: exactly K steps, device events, max over ranks -------------------------------------
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler:
+        sampler.arm(True)
+    e_beg.record(stream)
+    for k in range(args.steps):
+        step(evs[k])
+    e_end.record(stream)
+    sync_all()
+    total_ms = e_beg.elapsed_time(e_end)
+    # keep the identical load running ~1.5 s so NVML (10 ms period) sees the clocks this workload runs at
+    if sampler:
+        t_hold = time.perf_counter()
+        while time.perf_counter() - t_hold < 1.5:
+            for _ in range(20):
+                step()
+            torch.cuda.synchronize()
+        sampler.arm(False)
+    sync_all()
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    filt_ms = [e[0].elapsed_time(e[1]) for e in evs]
+    nms_ms = [e[1].elapsed_time(e[2]) for e in evs]
+    m_mean = float(counts[:, 0].float().mean().item())
+
+    # ---- end-to-end: host (pinned) heads -> H2D -> kernels -> D2H of rows + counts, per step -------------------
+    host_heads = [torch.empty(t_.shape, dtype=t_.dtype, pin_memory=True).copy_(t_) for t_ in flat]
+    dev_heads = [torch.empty_like(t_) for t_ in flat]
+    host_dets = torch.empty((args.batch, max_det, 6), dtype=torch.float32, pin_memory=True)
+    host_cnt = torch.empty((args.batch,), dtype=torch.int32, pin_memory=True)
+    ptrs2 = _lib.head_pointer_array(dev_heads)
+
+    def e2e_step():
+        for d, h in zip(dev_heads, host_heads):
+            d.copy_(h, non_blocking=True)
+        launch(ptrs2)
+        launch_nms(ptrs2)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), flat_send)
+        host_dets.copy_(dets_dense, non_blocking=True)
+        host_cnt.copy_(cnt_view, non_blocking=True)
+        stream.synchronize()  # the caller reads the rows on the host after every call
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    sync_all()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    h2d = sum(t_.numel() * 4 for t_ in flat)
+    d2h = host_dets.numel() * 4 + host_cnt.numel() * 4
+
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        C = 80
+        n_read_ch = C + 1                      # class planes + objectness; box planes are not read by K1
+        algo_bytes = args.batch * (N * n_read_ch * 4 + m_mean * 8)
+        filt_mean_ms = statistics.mean(filt_ms)
+        achieved = algo_bytes / (filt_mean_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": world * args.batch * args.steps / (total_ms * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (+f64 IoU test)",
+            "data": "synthetic", "config": workload_config(args, world),
+            "clocks": clocks,
+            "e2e": {"value": world * args.batch * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": "host pinned head tensors -> ysb_filter_candidates + ysb_select_nms -> host rows/counts"},
+            "gpu_launches": 2 * args.steps,
+            "roofline": {"kernel": "k_filter_planes<4> (decode-sigmoid + filter + class pick + compaction)",
+                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "traffic": None,
+                         "algorithmic_bytes_per_launch": algo_bytes,
+                         "bytes_per_image": f"N*(C+1)*4 read + M*8 written = {N * n_read_ch * 4} + {m_mean * 8:.0f}",
+                         "launch_ms": filt_mean_ms},
+            "stages_ms": {"filter_compact": filt_mean_ms, "select_sort_nms": statistics.mean(nms_ms),
+                          "filter_p50": statistics.median(filt_ms), "nms_p50": statistics.median(nms_ms)},
+            "survivors_per_image": m_mean,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            v, dt = cpu_images_per_second(cpu_heads(args.cpu_images, args), 1)
+            line["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": f"{args.cpu_images} images of the same workload on 1 host thread ({dt:.1f} s): C/numpy port "
+                          "of the reference algorithm incl. the full greedy NMS loop (no early stop)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

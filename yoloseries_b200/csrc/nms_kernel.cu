@@ -42,6 +42,7 @@ struct NmsSmem {
     unsigned long long keep_mask;
     int n_sel;
     int sel_digit;
+    int sel_above;
     int out_count;
 };
 
@@ -69,8 +70,10 @@ __device__ __forceinline__ uint64_t norm_key(uint64_t key, uint32_t smin)
     return (static_cast<uint64_t>(static_cast<uint32_t>(key >> 32) - smin) << 32) | (key & 0xffffffffull);
 }
 
-// Block-wide: lower bound `lo` (normalised key space) such that 1 <= #{lo <= nk <= hi_incl} <= kTrancheCap,
-// taking as many keys as fit while stopping the radix descent once kMinTranche keys are covered.
+// Block-wide radix descent over the normalised keys: returns a lower bound `lo` such that the set
+// {lo <= nk <= hi_incl} holds at least kMinTranche keys (or everything that is left) and at most kTrancheCap.
+// The smallest such set at the coarsest digit that resolves it is taken: the NMS walk usually ends long before a
+// tranche is exhausted, so sorting more than it needs is wasted work.
 __device__ uint64_t select_lower_bound(NmsSmem &S, const uint64_t *__restrict__ keys, int M, uint32_t smin,
                                        uint64_t hi_incl, int nbits)
 {
@@ -82,74 +85,80 @@ __device__ uint64_t select_lower_bound(NmsSmem &S, const uint64_t *__restrict__ 
     int acc = 0;                                           // keys already covered above the path
     for (;;) {
         for (int i = tid; i < kBins; i += kThreads) S.hist[i] = 0;
+        if (tid == 0) { S.sel_digit = -1; S.n_sel = 0; S.sel_above = 0; }
         __syncthreads();
         const int top = sh + width;
-        for (int i = tid; i < M; i += kThreads) {
-            const uint64_t nk = norm_key(keys[i], smin);
-            if (nk <= hi_incl && (!have_prefix || (top >= 64 ? 0ull : (nk >> top)) == prefix))
-                atomicAdd(&S.hist[(nk >> sh) & ((1u << width) - 1u)], 1u);
+        const uint32_t dmask = (1u << width) - 1u;
+        for (int i0 = 0; i0 < M; i0 += 4 * kThreads) {
+            uint64_t kk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = i0 + q * kThreads + tid;
+                kk[q] = i < M ? __ldg(keys + i) : 0ull;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (i0 + q * kThreads + tid >= M) continue;
+                const uint64_t nk = norm_key(kk[q], smin);
+                if (nk <= hi_incl && (!have_prefix || (nk >> top) == prefix))
+                    atomicAdd(&S.hist[static_cast<uint32_t>(nk >> sh) & dmask], 1u);
+            }
         }
         __syncthreads();
-        // suffix sums: thread t owns bins 2t, 2t+1
+        // suffix sums S(d) = #keys with digit >= d; thread t owns digits 2t, 2t+1
         const uint32_t h0 = S.hist[2 * tid], h1 = S.hist[2 * tid + 1];
-        uint32_t part = h0 + h1;
-        uint32_t incl = part;  // inclusive suffix over threads >= tid
+        const uint32_t part = h0 + h1;
+        uint32_t incl = part;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t v = __shfl_down_sync(0xffffffffu, incl, d);
             if ((tid & 31) + d < 32) incl += v;
         }
         if ((tid & 31) == 0) S.warp_tmp[tid >> 5] = incl;
-        if (tid == 0) S.sel_digit = -1;
         __syncthreads();
-        uint32_t above = 0;  // sum over warps after mine
+        uint32_t above = 0;
         for (int w = (tid >> 5) + 1; w < kThreads / 32; ++w) above += S.warp_tmp[w];
-        const uint32_t s_hi = incl - part + above;  // S(2t+2): bins strictly above my pair
+        const uint32_t s_hi = incl - part + above;  // S(2t+2)
         const uint32_t s1 = s_hi + h1;              // S(2t+1)
         const uint32_t s0 = s1 + h0;                // S(2t)
-        const uint32_t room = static_cast<uint32_t>(kTrancheCap - acc);
-        // d* = smallest digit d with S(d) <= room  <=>  S(d) <= room < S(d-1)
-        if (s1 <= room && s0 > room) S.sel_digit = 2 * tid + 1;
-        else if (s_hi <= room && s1 > room) S.sel_digit = 2 * tid + 2;
+        const uint32_t need = static_cast<uint32_t>(kMinTranche > acc ? kMinTranche - acc : 0);
+        // d_a = largest digit with S(d_a) >= need
+        if (s1 >= need && s_hi < need) { S.sel_digit = 2 * tid + 1; S.n_sel = static_cast<int>(s1); S.sel_above = static_cast<int>(s_hi); }
+        else if (s0 >= need && s1 < need) { S.sel_digit = 2 * tid; S.n_sel = static_cast<int>(s0); S.sel_above = static_cast<int>(s1); }
         __syncthreads();
-        const int dstar = S.sel_digit < 0 ? 0 : S.sel_digit;  // -1: even S(0) fits -> whole bucket
-        // covered = acc + S(dstar)
-        if (tid == 0) S.n_sel = 0;
-        __syncthreads();
-        if (dstar == 0) {
-            return have_prefix ? (prefix << top) : 0ull;
-        }
-        // recompute S(dstar) (every thread the same value): owner thread publishes it
-        if (2 * tid + 1 == dstar) S.n_sel = static_cast<int>(s1);
-        if (2 * tid + 2 == dstar) S.n_sel = static_cast<int>(s_hi);
-        __syncthreads();
-        const int covered = acc + S.n_sel;
+        const int da = S.sel_digit, covered = acc + S.n_sel, abv = acc + S.sel_above;
         __syncthreads();
         const uint64_t base = have_prefix ? (prefix << top) : 0ull;
-        if (covered >= kMinTranche || sh == 0) return base | (static_cast<uint64_t>(dstar) << sh);
-        // descend into digit dstar-1
-        prefix = (have_prefix ? (prefix << width) : 0ull) | static_cast<uint64_t>(dstar - 1);
+        if (da < 0) return base;  // fewer than kMinTranche keys under this prefix: take them all
+        if (covered <= kTrancheCap || sh == 0) return base | (static_cast<uint64_t>(da) << sh);
+        // digit d_a alone overflows the tranche: refine inside it
+        prefix = (have_prefix ? (prefix << width) : 0ull) | static_cast<uint64_t>(da);
         have_prefix = true;
-        acc = covered;
+        acc = abv;
         const int nw = sh < kDigitBits ? sh : kDigitBits;
         sh -= nw;
         width = nw;
     }
 }
 
+// Descending bitonic sort of n2 (power of two, <= kTrancheCap) keys in shared memory.  Strides below 32 pairs are
+// resolved inside a warp's private 64-element window, so only a __syncwarp separates those stages.
 __device__ void bitonic_sort_desc(uint64_t *a, int n2)
 {
-    for (int k = 2; k <= n2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < (n2 >> 1); t += kThreads) {
-                const int i = ((t / j) * (j << 1)) + (t % j);
-                const int p = i + j;
+    const int half = n2 >> 1;
+    for (int k = 2, lk = 1; k <= n2; k <<= 1, ++lk) {
+        for (int j = k >> 1, lj = lk - 1; j > 0; j >>= 1, --lj) {
+            for (int t = threadIdx.x; t < half; t += kThreads) {
+                const int i = ((t >> lj) << (lj + 1)) | (t & (j - 1));
+                const int p = i | j;
                 const bool desc = (i & k) == 0;
                 const uint64_t x = a[i], y = a[p];
                 if ((x < y) == desc) { a[i] = y; a[p] = x; }
             }
-            __syncthreads();
+            // pairs of stride j < 32 handled by thread t touch only elements [64*(t/32), 64*(t/32)+64): warp-private
+            if (j > 32) __syncthreads(); else __syncwarp();
         }
+        __syncthreads();
     }
 }
 
@@ -192,23 +201,26 @@ k_select_nms(const __grid_constant__ Plan P, const uint64_t *__restrict__ keys_a
         if (M - processed > kTrancheCap) lo = select_lower_bound(S, keys, M, smin, hi_incl, nbits);
         if (tid == 0) S.n_sel = 0;
         __syncthreads();
-        for (int i0 = 0; i0 < M; i0 += kThreads) {
-            const int i = i0 + tid;
-            uint64_t key = 0;
-            bool in = false;
-            if (i < M) {
-                key = keys[i];
-                const uint64_t nk = norm_key(key, smin);
-                in = nk >= lo && nk <= hi_incl;
+        for (int i0 = 0; i0 < M; i0 += 4 * kThreads) {
+            uint64_t kk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = i0 + q * kThreads + tid;
+                kk[q] = i < M ? __ldg(keys + i) : 0ull;
             }
-            const unsigned bal = __ballot_sync(0xffffffffu, in);
-            if (bal) {
-                int base = 0;
-                if ((tid & 31) == 0) base = atomicAdd(&S.n_sel, __popc(bal));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (in) {
-                    const int at = base + __popc(bal & ((1u << (tid & 31)) - 1u));
-                    if (at < kTrancheCap) S.keys[at] = key;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint64_t nk = norm_key(kk[q], smin);
+                const bool in = (i0 + q * kThreads + tid < M) && nk >= lo && nk <= hi_incl;
+                const unsigned bal = __ballot_sync(0xffffffffu, in);
+                if (bal) {
+                    int base = 0;
+                    if ((tid & 31) == 0) base = atomicAdd(&S.n_sel, __popc(bal));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (in) {
+                        const int at = base + __popc(bal & ((1u << (tid & 31)) - 1u));
+                        if (at < kTrancheCap) S.keys[at] = kk[q];
+                    }
                 }
             }
         }
