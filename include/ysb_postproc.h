@@ -108,6 +108,8 @@ typedef struct ysb_params {
     float min_box_wh;          /* min_prediction_box_wh (v7 / FCOS remove_small_boxes) */
     int32_t pre_nms_topk;      /* FCOS pre_nms_topk */
     int32_t thresh_with_ctr;   /* FCOS thresh_with_ctr */
+    int32_t decoded_rows;      /* DECODED_ROWS input only: rows per image when it is not the family's own N
+                                  (e.g. the concatenation of three TTA passes, eval_yolov5.py:152-179); 0 = N */
 } ysb_params;
 
 int ysb_abi_version(void);

@@ -1,0 +1,135 @@
+"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol include/ysb_postproc.h declares,
+validates arguments and reports sizes -- no compute call is made (there is no GPU in the build container)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ysb_postproc.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from yoloseries_b200 import _lib, build
+    build.build()
+    return _lib.load()
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ysb_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(lib):
+    from yoloseries_b200 import _lib
+    names = declared_symbols()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert sorted(_lib.EXPORTED_SYMBOLS) == names, "ctypes signature table out of sync with the header"
+
+
+def test_struct_layout_matches_header(lib):
+    """sizeof(ysb_params) as ctypes sees it must equal what the C compiler sees."""
+    import subprocess
+    import tempfile
+    from yoloseries_b200._lib import YsbParams
+    src = '#include <stdio.h>\n#include "ysb_postproc.h"\nint main(){printf("%zu %zu %zu", sizeof(ysb_params), ' \
+          '__builtin_offsetof(ysb_params, iou_thr), __builtin_offsetof(ysb_params, decoded_rows));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        size, off_iou, off_rows = map(int, subprocess.check_output([exe]).split())
+    assert ctypes.sizeof(YsbParams) == size
+    assert YsbParams.iou_thr.offset == off_iou
+    assert YsbParams.decoded_rows.offset == off_rows
+
+
+def _v5_params(**over):
+    import torch
+    from yoloseries_b200 import engine
+    import oracle
+    hyp = oracle.default_hyp()
+    hyp.update(over)
+    return engine.make_params("yolov5", hyp, 4, 640, 640, [(80, 80), (40, 40), (20, 20)],
+                              anchors=torch.tensor([[[10, 13], [16, 30], [33, 23]], [[30, 61], [62, 45], [59, 119]],
+                                                    [[116, 90], [156, 198], [373, 326]]]))
+
+
+def test_num_candidates_and_workspace(lib):
+    p = _v5_params()
+    n, rw, ws = ctypes.c_int64(), ctypes.c_int32(), ctypes.c_size_t()
+    assert lib.ysb_num_candidates(ctypes.byref(p), ctypes.byref(n), ctypes.byref(rw)) == 0
+    assert (n.value, rw.value) == (25200, 85)
+    assert lib.ysb_postprocess_workspace_bytes(ctypes.byref(p), ctypes.byref(ws)) == 0
+    assert ws.value >= 4 * 25200 * 8 + 4 * 16
+    assert abs(p.anchor[0][0][0] - 10 / 8) < 1e-7 and abs(p.anchor[2][2][1] - 326 / 32) < 1e-7
+
+
+@pytest.mark.parametrize("family,img,expect", [("yolox", 640, 8400), ("yolov8", 640, 34000), ("fcos", 640, 8525),
+                                               ("retinanet", 640, 76725), ("yolov5", 1280, 100800)])
+def test_candidate_counts_of_baseline_configs(lib, family, img, expect):
+    import torch
+    import oracle
+    from yoloseries_b200 import engine, synth
+    hyp = oracle.default_hyp()
+    shapes = None if family.startswith("retinanet") else synth.level_shapes(family, img, img)
+    anchors = torch.tensor(synth.V5_ANCHORS_PX) if family == "yolov5" else None
+    p = engine.make_params(family, hyp, 1, img, img, shapes, anchors=anchors)
+    n = ctypes.c_int64()
+    assert lib.ysb_num_candidates(ctypes.byref(p), ctypes.byref(n), None) == 0
+    assert n.value == expect == synth.num_candidates(family, img, img)
+
+
+def test_argument_validation(lib):
+    from yoloseries_b200 import _lib
+    n = ctypes.c_int64()
+    assert lib.ysb_num_candidates(None, ctypes.byref(n), None) == _lib.YSB_ERR_BAD_ARG
+    p = _v5_params()
+    p.family = 99
+    assert lib.ysb_num_candidates(ctypes.byref(p), ctypes.byref(n), None) == _lib.YSB_ERR_BAD_ARG
+    p = _v5_params(max_predictions_per_img=5000)
+    assert lib.ysb_num_candidates(ctypes.byref(p), ctypes.byref(n), None) == _lib.YSB_ERR_LIMIT
+    p = _v5_params(mutil_label=True)
+    assert lib.ysb_num_candidates(ctypes.byref(p), ctypes.byref(n), None) == _lib.YSB_ERR_UNSUPPORTED
+    p = _v5_params()
+    assert lib.ysb_postprocess(ctypes.byref(p), None, 3, None, 0, None, None, None, None) == _lib.YSB_ERR_BAD_ARG
+    ws = ctypes.c_size_t()
+    assert lib.ysb_nms_workspace_bytes(-1, ctypes.byref(ws)) == _lib.YSB_ERR_BAD_ARG
+    assert lib.ysb_nms_workspace_bytes(10 ** 9, ctypes.byref(ws)) == _lib.YSB_ERR_LIMIT
+    assert lib.ysb_status_string(_lib.YSB_ERR_WORKSPACE) == b"workspace too small"
+    with pytest.raises(ValueError):
+        _lib.check(_lib.YSB_ERR_BAD_ARG, "x")
+    with pytest.raises(NotImplementedError):
+        _lib.check(_lib.YSB_ERR_UNSUPPORTED, "x")
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, not compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import numpy as np
+    from yoloseries_b200.utils import numba_nms
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        numba_nms(np.zeros((3, 4), np.float32), np.ones(3, np.float32), 0.5)
+    from yoloseries_b200.engine import PostProcessor
+    import oracle
+    pp = PostProcessor("yolov5", oracle.default_hyp(), anchors=torch.tensor([[[1, 1]] * 3] * 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pp.run([torch.zeros(1, 255, 8, 8), torch.zeros(1, 255, 4, 4), torch.zeros(1, 255, 2, 2)], 64, 64)
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under yoloseries_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "yoloseries_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(d, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{f} imports the oracle"

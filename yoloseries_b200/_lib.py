@@ -54,6 +54,7 @@ class YsbParams(ctypes.Structure):
         ("min_box_wh", ctypes.c_float),
         ("pre_nms_topk", ctypes.c_int32),
         ("thresh_with_ctr", ctypes.c_int32),
+        ("decoded_rows", ctypes.c_int32),
     ]
 
 

@@ -97,6 +97,8 @@ static int build_plan(const ysb_params *p, const void *const *d_heads, int num_h
         n += static_cast<int64_t>(A) * lv.hw;
         if (n > YSB_MAX_CANDIDATES) return YSB_ERR_LIMIT;
     }
+    if (p->input_kind == YSB_INPUT_DECODED_ROWS && p->decoded_rows > 0) n = p->decoded_rows;
+    if (p->decoded_rows < 0 || n > YSB_MAX_CANDIDATES) return YSB_ERR_LIMIT;
     P.N = static_cast<int>(n);
 
     // ---- per-family operators and layouts ---------------------------------------------

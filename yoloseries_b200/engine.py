@@ -63,7 +63,7 @@ def _level_shapes(family, flat, num_class):
 
 
 def make_params(family, hyp, batch, img_h, img_w, level_shapes=None, anchors=None, input_kind=_lib.INPUT_RAW_HEADS,
-                compute_metric=False, num_anchors=None):
+                compute_metric=False, num_anchors=None, decoded_rows=0):
     """Build ``ysb_params`` from the reference's flat ``hyp`` dict (SURVEY.md section 5 lists the keys)."""
     p = YsbParams()
     p.family = _lib.FAMILY_IDS[family]
@@ -84,6 +84,7 @@ def make_params(family, hyp, batch, img_h, img_w, level_shapes=None, anchors=Non
     p.pre_nms_topk = int(hyp.get("pre_nms_topk", 1000))
     p.thresh_with_ctr = int(bool(hyp.get("thresh_with_ctr", True)))
     p.dfl_bins = int(hyp.get("reg", 16))
+    p.decoded_rows = int(decoded_rows)
     scale = hyp.get("tar_box_scale_factor", [0.1, 0.1, 0.2, 0.2])
     for i in range(4):
         p.reg_scale[i] = float(scale[i])
@@ -165,11 +166,12 @@ class PostProcessor:
             strides = _FIXED_STRIDES.get(self.family) or ((4, 8, 16, 32) if self.family == "yolov8" else (8, 16, 32))
             shapes = [(img_h // s, img_w // s) for s in strides]
         na = flat[0].shape[1] if (self.family == "yolox" and input_kind == _lib.INPUT_RAW_HEADS) else None
-        key = (batch, img_h, img_w, input_kind, tuple(shapes or ()), dev.index, na)
+        rows = int(flat[0].shape[1]) if input_kind == _lib.INPUT_DECODED_ROWS else 0
+        key = (batch, img_h, img_w, input_kind, tuple(shapes or ()), dev.index, na, rows)
         ent = self._cache.get(key)
         if ent is None:
             params = make_params(self.family, self.hyp, batch, img_h, img_w, shapes, self.anchors, input_kind,
-                                 self.compute_metric, na)
+                                 self.compute_metric, na, rows)
             n = ctypes.c_int64()
             rw = ctypes.c_int32()
             _lib.check(self._lib.ysb_num_candidates(ctypes.byref(params), ctypes.byref(n), ctypes.byref(rw)),
@@ -205,8 +207,8 @@ class PostProcessor:
         batch = flat[0].shape[0]
         kind = _lib.INPUT_DECODED_ROWS if decoded else _lib.INPUT_RAW_HEADS
         ent = self._prepare(flat, batch, img_h, img_w, kind)
-        if decoded and (flat[0].shape[1] != ent["N"] or flat[0].shape[2] != ent["row_w"]):
-            raise ValueError(f"decoded tensor must be (b, {ent['N']}, {ent['row_w']}), got {tuple(flat[0].shape)}")
+        if decoded and (flat[0].dim() != 3 or flat[0].shape[2] != ent["row_w"]):
+            raise ValueError(f"decoded tensor must be (b, N, {ent['row_w']}), got {tuple(flat[0].shape)}")
         out = ent["out"]
         ptrs = _lib.head_pointer_array(flat)
         ws = ent["workspace"]

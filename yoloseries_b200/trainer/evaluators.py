@@ -1,0 +1,201 @@
+"""Drop-in mirrors of the reference evaluators (trainer/eval_*.py): same constructors, same methods, same outputs.
+
+    YOLOV5Evaluator(yolo, anchors, hyp, compute_metric=False)      trainer/eval_yolov5.py:10-42
+    YOLOV7Evaluator(yolo, anchors, hyp, compute_metric=False)      trainer/eval_yolov7.py
+    YOLOXEvaluator(yolo, hyp, compute_metric=False)                trainer/eval_yolox.py:11-41
+    YOLOV8Evaluator(yolo, hyp, compute_metric=False)               trainer/eval_yolov8.py:11-38
+    RetinaNetEvaluator(model, hyp, compute_metric=False)           trainer/eval_retinanet.py:9-20
+    RetinaNetEvaluatorExperiment(model, hyp, compute_metric=False) trainer/eval_retinanet_experiment.py
+    FCOSEvaluator(model, hyp, compute_metric=False)                trainer/eval_fcos.py:12-38
+
+``__call__(inputs)`` returns ``list[Tensor(K,6) | None]`` -- CPU float32 rows [xmin, ymin, xmax, ymax, score, cls] in NMS
+keep order, ``None`` where the reference returns ``None``.  Without TTA the model's raw heads go
+straight into the fused CUDA path (no (b, N, C') tensor is ever written); ``do_inference`` / ``numba_nms`` remain
+available separately with the reference's signatures.  Everything heavy runs in libysb_postproc.so; there is no CPU path.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from ..engine import PostProcessor
+
+__all__ = ["YOLOV5Evaluator", "YOLOV7Evaluator", "YOLOXEvaluator", "YOLOV8Evaluator", "RetinaNetEvaluator",
+           "RetinaNetEvaluatorExperiment", "FCOSEvaluator"]
+
+
+class _Evaluator:
+    family = None
+    _box_cols_xywh = True   # decoded rows carry [cx, cy, w, h] (True) or [x1, y1, x2, y2] (False) -- matters for TTA flips
+
+    def _setup(self, model, hyp, compute_metric, anchors=None):
+        self.hyp = hyp
+        self.device = hyp["device"]
+        self.num_class = hyp["num_class"]
+        self.use_tta = hyp["use_tta"]
+        self._model = model
+        self.anchors = anchors
+        pre = "compute_metric_" if compute_metric else ""
+        self.iou_threshold = hyp[pre + "iou_threshold"]
+        self.cls_threshold = hyp[pre + "cls_threshold"]
+        if (pre + "conf_threshold") in hyp:
+            self.conf_threshold = hyp[pre + "conf_threshold"]
+        self._pp = PostProcessor(self.family, hyp, anchors=anchors, compute_metric=compute_metric)
+
+    # ---- reference API -------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def __call__(self, inputs):
+        if self.use_tta:
+            merged, independent = self.test_time_augmentation(inputs)
+            if self.hyp.get("wfb", False):
+                raise NotImplementedError("weighted-box-fusion (hyp['wfb']) is a 'next' row (SURVEY.md 8f rank 3)")
+            outs = self.numba_nms(merged)
+            return [torch.from_numpy(x) if x is not None else None for x in outs]
+        heads = self._model(inputs)
+        out = self._pp.run(heads, inputs.size(2), inputs.size(3))
+        return self._pp.to_list(out)
+
+    @torch.no_grad()
+    def do_inference(self, inputs):
+        """model forward + decode -> (b, N, C') float32 on the heads' device (one CUDA kernel, ysb_decode)."""
+        heads = self._model(inputs)
+        return self._pp.decode(heads, inputs.size(2), inputs.size(3))
+
+    def numba_nms(self, preds_out):
+        """(b, N, C') decoded tensor -> list[ndarray(K,6) float32 | None] (the reference's CPU numba path, on the GPU)."""
+        if isinstance(preds_out, np.ndarray):
+            preds_out = torch.from_numpy(preds_out)
+        preds = preds_out.detach().to(torch.float32)
+        if preds.device.type != "cuda":
+            preds = preds.cuda()
+        preds = preds.contiguous()
+        h, w = self.hyp["input_img_size"]
+        out = self._pp.run(preds, int(h), int(w), decoded=True)
+        return self._pp.to_list(out, as_numpy=True)
+
+    def do_nms(self, preds_out):
+        """Dead code in the reference (no caller; raises IndexError for iou_type='iou').  Mirrored
+        with the live path's semantics, returning tensors."""
+        return [torch.from_numpy(x) if x is not None else None for x in self.numba_nms(preds_out)]
+
+    # ---- TTA: the reference's own torch expressions, kept on the device ----------------------
+    def test_time_augmentation(self, inputs):
+        img_h, img_w = inputs.size(2), inputs.size(3)
+        b0 = self._pp_box_col()
+        preds_all = []
+        for s, f in zip([1, 0.83, 0.67], [None, 2, 3]):
+            img = inputs.flip(dims=(f,)) if f else inputs
+            img = self.scale_img(img, s)
+            p = self.do_inference(img)
+            p[..., b0:b0 + 4] /= s
+            if self._box_cols_xywh:
+                if f == 2:
+                    p[..., b0 + 1] = img_h - p[..., b0 + 1]
+                if f == 3:
+                    p[..., b0 + 0] = img_w - p[..., b0 + 0]
+            else:
+                if f == 2:
+                    ymin, ymax = img_h - p[..., b0 + 3], img_h - p[..., b0 + 1]
+                    p[..., b0 + 1], p[..., b0 + 3] = ymin, ymax
+                if f == 3:
+                    xmin, xmax = img_w - p[..., b0 + 2], img_w - p[..., b0 + 0]
+                    p[..., b0 + 0], p[..., b0 + 2] = xmin, xmax
+            preds_all.append(p)
+        return torch.cat(preds_all, dim=1).contiguous(), preds_all
+
+    def _pp_box_col(self):
+        return self.num_class if self.family.startswith("retinanet") else 0
+
+    @staticmethod
+    def scale_img(img, scale_factor):
+        """trainer/eval_yolov5.py:211-227 (identical in every evaluator)."""
+        if scale_factor == 1.0:
+            return img
+        h, w = img.shape[2], img.shape[3]
+        new_h, new_w = int(scale_factor * h), int(scale_factor * w)
+        img = F.interpolate(img, size=(new_h, new_w), align_corners=False, mode="bilinear")
+        out_h, out_w = int(np.ceil(h / 32) * 32), int(np.ceil(w / 32) * 32)
+        return F.pad(img, [0, out_w - new_w, 0, out_h - new_h], value=0.447)
+
+
+class YOLOV5Evaluator(_Evaluator):
+    family = "yolov5"
+
+    def __init__(self, yolo, anchors, hyp, compute_metric=False):
+        self.yolo = yolo
+        self.anchor_num = anchors.size(1)
+        self.num_stage = len(anchors)
+        self.ds_scales = [8, 16, 32]
+        self.inp_h, self.inp_w = hyp["input_img_size"]
+        self._setup(yolo, hyp, compute_metric, anchors)
+
+
+class YOLOV7Evaluator(_Evaluator):
+    family = "yolov7"
+
+    def __init__(self, yolo, anchors, hyp, compute_metric=False):
+        self.yolo = yolo
+        self.anchor_num = anchors.size(1)
+        self.num_stage = len(anchors)
+        self.ds_scales = [8, 16, 32]
+        self.inp_h, self.inp_w = hyp["input_img_size"]
+        self._setup(yolo, hyp, compute_metric, anchors)
+
+
+class YOLOXEvaluator(_Evaluator):
+    family = "yolox"
+
+    def __init__(self, yolo, hyp, compute_metric=False):
+        self.yolo = yolo
+        self.num_stage = hyp.get("num_stage", 3)
+        self.ds_scales = [8, 16, 32]
+        self.inp_h, self.inp_w = hyp["input_img_size"]
+        self._setup(yolo, hyp, compute_metric)
+
+
+class YOLOV8Evaluator(_Evaluator):
+    family = "yolov8"
+    _box_cols_xywh = False
+
+    def __init__(self, yolo, hyp, compute_metric=False):
+        self.yolo = yolo
+        self.inp_h, self.inp_w = hyp["input_img_size"]
+        self.reg = hyp["reg"]
+        self._setup(yolo, hyp, compute_metric)
+
+
+class RetinaNetEvaluator(_Evaluator):
+    family = "retinanet"
+    _box_cols_xywh = False
+
+    def __init__(self, model, hyp, compute_metric=False):
+        self.model = model
+        self.enable_tta = hyp["use_tta"]
+        self.iou_loss_scale = hyp["tar_box_scale_factor"]
+        self._setup(model, hyp, compute_metric)
+
+    def numba_nms(self, preds_out):
+        # the reference evaluator has no hyp['input_img_size'] dependency: anchors follow the image size, and the
+        # decoded tensor carries no geometry, so only its row count matters here
+        if isinstance(preds_out, np.ndarray):
+            preds_out = torch.from_numpy(preds_out)
+        preds = preds_out.detach().to(torch.float32)
+        if preds.device.type != "cuda":
+            preds = preds.cuda()
+        h, w = self.hyp.get("input_img_size", (640, 640))
+        out = self._pp.run(preds.contiguous(), int(h), int(w), decoded=True)
+        return self._pp.to_list(out, as_numpy=True)
+
+
+class RetinaNetEvaluatorExperiment(RetinaNetEvaluator):
+    family = "retinanet_exp"
+
+
+class FCOSEvaluator(_Evaluator):
+    family = "fcos"
+    _box_cols_xywh = False
+
+    def __init__(self, model, hyp, compute_metric=False):
+        self.model = model
+        self.ds_scales = [8, 16, 32, 64, 128]
+        self.inp_h, self.inp_w = hyp["input_img_size"]
+        self._setup(model, hyp, compute_metric)
