@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--family", default="yolov5")
     ap.add_argument("--img", type=int, default=640)
     ap.add_argument("--dist", default="dense", choices=["dense", "sparse", "crowd"])
+    ap.add_argument("--pipeline", type=int, default=1, help="overlap the NMS kernel of batch i with the filter kernel of batch i+1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-images", type=int, default=2, help="images in the bounded CPU-baseline sample")
     return ap.parse_args()
@@ -222,40 +223,72 @@ def run_ours(args):
     ent = pp._prepare(flat, args.batch, args.img, args.img, _lib.INPUT_RAW_HEADS)
     lib = _lib.load()
     params, N, out = ent["params"], ent["N"], ent["out"]
-    keys = torch.empty((args.batch, N), dtype=torch.int64, device=dev)
-    counts = torch.zeros((args.batch, 4), dtype=torch.int32, device=dev)
     ptrs = _lib.head_pointer_array(flat)
     max_det = params.max_det
-    # One flat buffer per rank = [rows (b, max_det, 6) f32 | counts (b) i32]: the NMS kernel writes straight into it
-    # and, at N > 1, it is the (fixed-stride, no size pre-exchange) send buffer of the all-gather.
     n_row_f = args.batch * max_det * 6
-    flat_send = torch.zeros(n_row_f + args.batch, dtype=torch.float32, device=dev)
-    dets_dense = flat_send[:n_row_f].view(args.batch, max_det, 6)
-    cnt_view = flat_send[n_row_f:].view(torch.int32)
-    gathered = torch.empty((world, n_row_f + args.batch), dtype=torch.float32, device=dev) if world > 1 else None
+
+    class Slot:
+        """Intermediates + outputs of one in-flight batch.  `flat_send` = [rows (b, max_det, 6) f32 | counts (b) i32]:
+        the NMS kernel writes straight into it and, at N > 1, it is the fixed-stride send buffer of the all-gather."""
+
+        def __init__(self):
+            self.keys = torch.empty((args.batch, N), dtype=torch.int64, device=dev)
+            self.counts = torch.zeros((args.batch, 4), dtype=torch.int32, device=dev)
+            self.flat_send = torch.zeros(n_row_f + args.batch, dtype=torch.float32, device=dev)
+            self.dets = self.flat_send[:n_row_f].view(args.batch, max_det, 6)
+            self.cnt = self.flat_send[n_row_f:].view(torch.int32)
+            self.idx = torch.empty((args.batch, max_det), dtype=torch.int32, device=dev)
+            self.gathered = torch.empty((world, n_row_f + args.batch), dtype=torch.float32, device=dev) if world > 1 else None
+            self.filtered = torch.cuda.Event()
+            self.done = torch.cuda.Event()
+
+    # Two slots + two streams: the select/sort/NMS kernel of batch i (64 CTAs, latency-bound) runs on the side stream
+    # while the HBM-bound filter kernel of batch i+1 streams on the main one.  --pipeline 0 serialises them.
+    slots = [Slot(), Slot()] if args.pipeline else [Slot()]
     stream = torch.cuda.current_stream()
-    sp = ctypes.c_void_p(stream.cuda_stream)
+    side = torch.cuda.Stream(device=dev) if args.pipeline else stream
 
-    def launch(head_ptrs):
-        _lib.check(lib.ysb_filter_candidates(ctypes.byref(params), head_ptrs, len(flat), keys.data_ptr(), N,
-                                             counts.data_ptr(), sp), "ysb_filter_candidates")
+    def launch_filter(head_ptrs, sl, st):
+        _lib.check(lib.ysb_filter_candidates(ctypes.byref(params), head_ptrs, len(flat), sl.keys.data_ptr(), N,
+                                             sl.counts.data_ptr(), ctypes.c_void_p(st.cuda_stream)),
+                   "ysb_filter_candidates")
 
-    def launch_nms(head_ptrs):
-        _lib.check(lib.ysb_select_nms(ctypes.byref(params), head_ptrs, len(flat), keys.data_ptr(), N,
-                                      counts.data_ptr(), dets_dense.data_ptr(), out.det_idx.data_ptr(),
-                                      cnt_view.data_ptr(), sp), "ysb_select_nms")
+    def launch_nms(head_ptrs, sl, st):
+        _lib.check(lib.ysb_select_nms(ctypes.byref(params), head_ptrs, len(flat), sl.keys.data_ptr(), N,
+                                      sl.counts.data_ptr(), sl.dets.data_ptr(), sl.idx.data_ptr(),
+                                      sl.cnt.data_ptr(), ctypes.c_void_p(st.cuda_stream)), "ysb_select_nms")
 
-    def step(ev=None):
+    step_no = [0]
+
+    def step(ev=None, head_ptrs=None):
+        head_ptrs = head_ptrs or ptrs
+        sl = slots[step_no[0] % len(slots)]
+        step_no[0] += 1
+        if args.pipeline:
+            stream.wait_event(sl.done)       # the slot's previous batch has left the NMS stage
         if ev:
             ev[0].record(stream)
-        launch(ptrs)
+        launch_filter(head_ptrs, sl, stream)
         if ev:
             ev[1].record(stream)
-        launch_nms(ptrs)
+        if args.pipeline:
+            sl.filtered.record(stream)
+            side.wait_event(sl.filtered)
         if ev:
-            ev[2].record(stream)
+            ev[2].record(side)
+        launch_nms(head_ptrs, sl, side)
+        if ev:
+            ev[3].record(side)
         if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), flat_send)
+            with torch.cuda.stream(side):
+                dist.all_gather_into_tensor(sl.gathered.view(-1), sl.flat_send)
+        if args.pipeline:
+            sl.done.record(side)
+        return sl
+
+    def drain():
+        if args.pipeline:
+            stream.wait_stream(side)
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -271,13 +304,14 @@ def run_ours(args):
         step()
     sync_all()
     # ---- timed region: exactly K steps, device events, max over ranks -------------------------------------
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if sampler:
         sampler.arm(True)
     e_beg.record(stream)
     for k in range(args.steps):
         step(evs[k])
+    drain()
     e_end.record(stream)
     sync_all()
     total_ms = e_beg.elapsed_time(e_end)
@@ -287,6 +321,7 @@ def run_ours(args):
         while time.perf_counter() - t_hold < 1.5:
             for _ in range(20):
                 step()
+            drain()
             torch.cuda.synchronize()
         sampler.arm(False)
     sync_all()
@@ -295,8 +330,8 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     filt_ms = [e[0].elapsed_time(e[1]) for e in evs]
-    nms_ms = [e[1].elapsed_time(e[2]) for e in evs]
-    m_mean = float(counts[:, 0].float().mean().item())
+    nms_ms = [e[2].elapsed_time(e[3]) for e in evs]
+    m_mean = float(slots[0].counts[:, 0].float().mean().item())
 
     # ---- end-to-end: host (pinned) heads -> H2D -> kernels -> D2H of rows + counts, per step -------------------
     host_heads = [torch.empty(t_.shape, dtype=t_.dtype, pin_memory=True).copy_(t_) for t_ in flat]
@@ -308,12 +343,10 @@ def run_ours(args):
     def e2e_step():
         for d, h in zip(dev_heads, host_heads):
             d.copy_(h, non_blocking=True)
-        launch(ptrs2)
-        launch_nms(ptrs2)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), flat_send)
-        host_dets.copy_(dets_dense, non_blocking=True)
-        host_cnt.copy_(cnt_view, non_blocking=True)
+        sl = step(None, ptrs2)
+        drain()
+        host_dets.copy_(sl.dets, non_blocking=True)
+        host_cnt.copy_(sl.cnt, non_blocking=True)
         stream.synchronize()  # the caller reads the rows on the host after every call
 
     e2e_steps = max(3, min(args.steps, 10))
@@ -360,6 +393,7 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": algo_bytes,
                          "bytes_per_image": f"N*(C+1)*4 read + M*8 written = {N * n_read_ch * 4} + {m_mean * 8:.0f}",
                          "launch_ms": filt_mean_ms},
+            "pipeline": bool(args.pipeline),
             "stages_ms": {"filter_compact": filt_mean_ms, "select_sort_nms": statistics.mean(nms_ms),
                           "filter_p50": statistics.median(filt_ms), "nms_p50": statistics.median(nms_ms)},
             "survivors_per_image": m_mean,

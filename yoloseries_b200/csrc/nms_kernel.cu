@@ -25,6 +25,7 @@ constexpr int kDigitBits = 11;
 constexpr int kBins = 1 << kDigitBits;
 constexpr int kChunk = 64;
 constexpr int kMaxKeep = YSB_MAX_DET_LIMIT;
+constexpr int kKeyBatch = 8;  // independent 64-bit key loads in flight per thread in the selection passes
 
 struct NmsSmem {
     uint64_t keys[kTrancheCap];
@@ -35,7 +36,9 @@ struct NmsSmem {
     float4 kept_raw[kMaxKeep];
     uint8_t kept_flag[kMaxKeep];
     OffBox chunk_box[kChunk];
-    uint64_t chunk_mask[kChunk];
+    uint64_t chunk_mask[kChunk];   // row i: later candidates j > i that i suppresses
+    unsigned int chunk_pred[kChunk][2];  // row i: earlier candidates j < i that suppress i (lo/hi words)
+    float area[kTrancheCap];       // post-filter: areas of the offset boxes
     uint8_t chunk_alive[kChunk];
     uint32_t warp_tmp[kThreads / 32];
     unsigned long long sel_lo;
@@ -89,15 +92,15 @@ __device__ uint64_t select_lower_bound(NmsSmem &S, const uint64_t *__restrict__ 
         __syncthreads();
         const int top = sh + width;
         const uint32_t dmask = (1u << width) - 1u;
-        for (int i0 = 0; i0 < M; i0 += 4 * kThreads) {
-            uint64_t kk[4];
+        for (int i0 = 0; i0 < M; i0 += kKeyBatch * kThreads) {
+            uint64_t kk[kKeyBatch];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < kKeyBatch; ++q) {
                 const int i = i0 + q * kThreads + tid;
                 kk[q] = i < M ? __ldg(keys + i) : 0ull;
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < kKeyBatch; ++q) {
                 if (i0 + q * kThreads + tid >= M) continue;
                 const uint64_t nk = norm_key(kk[q], smin);
                 if (nk <= hi_incl && (!have_prefix || (nk >> top) == prefix))
@@ -201,15 +204,15 @@ k_select_nms(const __grid_constant__ Plan P, const uint64_t *__restrict__ keys_a
         if (M - processed > kTrancheCap) lo = select_lower_bound(S, keys, M, smin, hi_incl, nbits);
         if (tid == 0) S.n_sel = 0;
         __syncthreads();
-        for (int i0 = 0; i0 < M; i0 += 4 * kThreads) {
-            uint64_t kk[4];
+        for (int i0 = 0; i0 < M; i0 += kKeyBatch * kThreads) {
+            uint64_t kk[kKeyBatch];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < kKeyBatch; ++q) {
                 const int i = i0 + q * kThreads + tid;
                 kk[q] = i < M ? __ldg(keys + i) : 0ull;
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < kKeyBatch; ++q) {
                 const uint64_t nk = norm_key(kk[q], smin);
                 const bool in = (i0 + q * kThreads + tid < M) && nk >= lo && nk <= hi_incl;
                 const unsigned bal = __ballot_sync(0xffffffffu, in);
@@ -264,6 +267,8 @@ k_select_nms(const __grid_constant__ Plan P, const uint64_t *__restrict__ keys_a
                 const unsigned bal = __ballot_sync(0xffffffffu, sup);
                 const unsigned half = (tid & 16) ? 0xffff0000u : 0x0000ffffu;
                 if (sub == 0 && j < kChunk) {
+                    S.chunk_pred[j][0] = 0u;
+                    S.chunk_pred[j][1] = 0u;
                     // a zero score is never picked by "while sum > 0" (utils/nms.py:16): it is neither kept nor a suppressor
                     S.chunk_alive[j] = valid && !(bal & half) && score > 0.0f;
                     if (valid) S.chunk_box[j] = ob;
@@ -281,6 +286,7 @@ k_select_nms(const __grid_constant__ Plan P, const uint64_t *__restrict__ keys_a
                         const int j = sub * 4 + q;
                         if (j > i && j < cn && S.chunk_alive[j] && pair_hit<ARRAY>(bi, S.chunk_box[j], thr, aa)) {
                             if (j < 32) lo32 |= 1u << j; else hi32 |= 1u << (j - 32);
+                            atomicOr(&S.chunk_pred[j][i >> 5], 1u << (i & 31));  // rare: suppression inside a chunk
                         }
                     }
                 }
@@ -298,20 +304,27 @@ k_select_nms(const __grid_constant__ Plan P, const uint64_t *__restrict__ keys_a
                 const bool conflict = (((alive >> tid) & 1ull) && (S.chunk_mask[tid] & alive)) ||
                                       (((alive >> (tid + 32)) & 1ull) && (S.chunk_mask[tid + 32] & alive));
                 const unsigned any = __ballot_sync(0xffffffffu, conflict);
-                if (tid == 0) {
-                    uint64_t keep = 0;
-                    const int room = max_det - kept;
-                    if (!any) {
-                        keep = alive;
-                    } else {
-                        uint64_t rem = alive;
-                        while (rem) {
-                            const int i = __ffsll(static_cast<long long>(rem)) - 1;
-                            keep |= 1ull << i;
-                            rem &= ~(1ull << i);
-                            rem &= ~S.chunk_mask[i];
-                        }
+                uint64_t keep = alive;
+                if (any) {
+                    // Greedy resolution without a serial walk: a candidate is decided as soon as all of its earlier
+                    // in-chunk suppressors are decided -- kept if none of them was kept, dropped otherwise.  The
+                    // lowest undecided candidate is always decidable, so this ends; typical chunks need 2-4 rounds.
+                    const uint64_t p0 = (static_cast<uint64_t>(S.chunk_pred[tid][1]) << 32 | S.chunk_pred[tid][0]) & alive;
+                    const uint64_t p1 = (static_cast<uint64_t>(S.chunk_pred[tid + 32][1]) << 32 | S.chunk_pred[tid + 32][0]) & alive;
+                    uint64_t U = alive, K = 0;
+                    while (U) {
+                        const bool in0 = (U >> tid) & 1ull, in1 = (U >> (tid + 32)) & 1ull;
+                        const bool sup0 = in0 && (p0 & K), sup1 = in1 && (p1 & K);
+                        const bool kp0 = in0 && !(p0 & K) && !(p0 & U), kp1 = in1 && !(p1 & K) && !(p1 & U);
+                        const uint64_t Rk = (static_cast<uint64_t>(__ballot_sync(0xffffffffu, kp1)) << 32) | __ballot_sync(0xffffffffu, kp0);
+                        const uint64_t Rs = (static_cast<uint64_t>(__ballot_sync(0xffffffffu, sup1)) << 32) | __ballot_sync(0xffffffffu, sup0);
+                        K |= Rk;
+                        U &= ~(Rk | Rs);
                     }
+                    keep = K;
+                }
+                if (tid == 0) {
+                    const int room = max_det - kept;
                     int cntk = __popcll(keep);
                     while (cntk > room) {  // drop the lowest-priority (highest index) keeps beyond max_det
                         keep &= ~(1ull << (63 - __clzll(static_cast<long long>(keep))));
@@ -354,6 +367,29 @@ k_select_nms(const __grid_constant__ Plan P, const uint64_t *__restrict__ keys_a
         // 1 < M < 3000 <= tranche capacity: the single tranche holds every survivor, boxes decoded for all
         const int warp = tid >> 5, lane = tid & 31;
         const int mm = min(n_tranche, limit);
+        if (!P.merge_boxes) {
+            // offset boxes + areas once per survivor (in place: the raw boxes of the kept rows live in kept_raw)
+            for (int j = tid; j < mm; j += kThreads) {
+                const uint64_t key = S.keys[j];
+                const float off = P.class_aware ? __fmul_rn(static_cast<float>(key_cls(key)), 4096.0f) : 0.0f;
+                const OffBox b = make_offbox(S.raw[j], off);
+                S.raw[j] = make_float4(b.x1, b.y1, b.x2, b.y2);
+                S.area[j] = b.area;
+            }
+            __syncthreads();
+            for (int r = warp; r < kept; r += kThreads / 32) {
+                const OffBox br = kept_box[r];
+                int c = 0;
+                for (int j = lane; j < mm; j += 32) {
+                    const float4 o = S.raw[j];
+                    OffBox bj;
+                    bj.x1 = o.x; bj.y1 = o.y; bj.x2 = o.z; bj.y2 = o.w; bj.area = S.area[j];
+                    c += iou_reaches<true>(br, bj, thr) ? 1 : 0;
+                }
+                c = __reduce_add_sync(0xffffffffu, c);
+                if (lane == 0) S.kept_flag[r] = c > 1;
+            }
+        } else {
         for (int r = warp; r < kept; r += kThreads / 32) {
             const OffBox br = kept_box[r];
             int c = 0;
@@ -364,34 +400,30 @@ k_select_nms(const __grid_constant__ Plan P, const uint64_t *__restrict__ keys_a
                 const float4 rj = S.raw[j];
                 if (iou_reaches<true>(br, make_offbox(rj, off), thr)) {
                     ++c;
-                    if (P.merge_boxes) {  // trainer/eval_retinanet.py:346-349 (float32 weights, float32 dot)
-                        const float w = key_score(key);
-                        ax = __fadd_rn(ax, __fmul_rn(w, rj.x));
-                        ay = __fadd_rn(ay, __fmul_rn(w, rj.y));
-                        az = __fadd_rn(az, __fmul_rn(w, rj.z));
-                        aw = __fadd_rn(aw, __fmul_rn(w, rj.w));
-                        ws = __fadd_rn(ws, w);
-                    }
+                    // trainer/eval_retinanet.py:346-349 (float32 weights, float32 dot)
+                    const float w = key_score(key);
+                    ax = __fadd_rn(ax, __fmul_rn(w, rj.x));
+                    ay = __fadd_rn(ay, __fmul_rn(w, rj.y));
+                    az = __fadd_rn(az, __fmul_rn(w, rj.z));
+                    aw = __fadd_rn(aw, __fmul_rn(w, rj.w));
+                    ws = __fadd_rn(ws, w);
                 }
             }
             c = __reduce_add_sync(0xffffffffu, c);
-            if (P.merge_boxes) {
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) {
-                    ax = __fadd_rn(ax, __shfl_xor_sync(0xffffffffu, ax, d));
-                    ay = __fadd_rn(ay, __shfl_xor_sync(0xffffffffu, ay, d));
-                    az = __fadd_rn(az, __shfl_xor_sync(0xffffffffu, az, d));
-                    aw = __fadd_rn(aw, __shfl_xor_sync(0xffffffffu, aw, d));
-                    ws = __fadd_rn(ws, __shfl_xor_sync(0xffffffffu, ws, d));
-                }
+            for (int d = 16; d > 0; d >>= 1) {
+                ax = __fadd_rn(ax, __shfl_xor_sync(0xffffffffu, ax, d));
+                ay = __fadd_rn(ay, __shfl_xor_sync(0xffffffffu, ay, d));
+                az = __fadd_rn(az, __shfl_xor_sync(0xffffffffu, az, d));
+                aw = __fadd_rn(aw, __shfl_xor_sync(0xffffffffu, aw, d));
+                ws = __fadd_rn(ws, __shfl_xor_sync(0xffffffffu, ws, d));
             }
             if (lane == 0) {
                 S.kept_flag[r] = c > 1;
-                if (P.merge_boxes) {
-                    const float den = __fadd_rn(ws, 1e-16f);
-                    S.kept_raw[r] = make_float4(__fdiv_rn(ax, den), __fdiv_rn(ay, den), __fdiv_rn(az, den), __fdiv_rn(aw, den));
-                }
+                const float den = __fadd_rn(ws, 1e-16f);
+                S.kept_raw[r] = make_float4(__fdiv_rn(ax, den), __fdiv_rn(ay, den), __fdiv_rn(az, den), __fdiv_rn(aw, den));
             }
+        }
         }
     } else {
         for (int r = tid; r < kept; r += kThreads) S.kept_flag[r] = 1;
