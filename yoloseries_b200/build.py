@@ -29,7 +29,7 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, extra_flags=()):
     if not force and not _stale():
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)
@@ -37,7 +37,7 @@ def build(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
-        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC, *FLAGS, *extra_flags, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -57,4 +57,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force=True, verbose="-v" in sys.argv))
+    print(build(force=True, verbose="-v" in sys.argv, extra_flags=[a for a in sys.argv[1:] if a.startswith("-D")]))

@@ -20,6 +20,10 @@ cudaError_t launch_pairwise_iou(const float *b1, int64_t n, const float *b2, int
 cudaError_t launch_elementwise_iou(const float *b1, int64_t n1, const float *b2, int64_t n2, int kind, float *out,
                                    cudaStream_t stream);
 
+#ifdef YSB_K2_TIMING
+cudaError_t debug_k2_timing(long long *host_out);
+#endif
+
 static thread_local int g_last_cuda_error = 0;
 
 static int cuda_status(cudaError_t e)
@@ -352,5 +356,9 @@ int ysb_elementwise_iou(const float *d_b1, int64_t n1, const float *d_b2, int64_
     if (!(n1 == n2 || n1 == 1)) return YSB_ERR_BAD_ARG;
     return cuda_status(launch_elementwise_iou(d_b1, n1, d_b2, n2, iou_kind, d_out, static_cast<cudaStream_t>(stream)));
 }
+
+#ifdef YSB_K2_TIMING
+int ysb_debug_k2_timing(long long *host_out) { return cuda_status(ysb::debug_k2_timing(host_out)); }
+#endif
 
 }  // extern "C"

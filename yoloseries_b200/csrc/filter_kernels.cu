@@ -27,6 +27,14 @@ __device__ __forceinline__ float4 ldg_stream4(const float *p)
                  : "l"(p));
     return v;
 }
+__device__ __forceinline__ float4 ldg_stream4_256(const float *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
 __device__ __forceinline__ float ldg_stream1(const float *p)
 {
     float v;
@@ -144,9 +152,9 @@ __device__ __forceinline__ void emit_keys(const uint64_t (&k)[VEC], unsigned okm
 // planes layout (NCHW heads: YOLOv5, YOLOX, YOLOv8, FCOS).  One thread = VEC consecutive positions of one
 // (image, anchor); per class plane a warp reads 32*VEC*4 contiguous bytes (512 B with 128-bit loads).
 // -------------------------------------------------------------------------------------------------------
-template <int VEC>
-__global__ void __launch_bounds__(256) k_filter_planes(const __grid_constant__ Plan P, uint64_t *__restrict__ keys,
-                                                       int64_t key_cap, int32_t *__restrict__ counts)
+template <int VEC, int U = 8, int THREADS = 256, int MINB = 1, int HINT = 0>
+__global__ void __launch_bounds__(THREADS, MINB) k_filter_planes(const __grid_constant__ Plan P, uint64_t *__restrict__ keys,
+                                                                 int64_t key_cap, int32_t *__restrict__ counts)
 {
     const int img = blockIdx.y;
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
@@ -176,14 +184,14 @@ __global__ void __launch_bounds__(256) k_filter_planes(const __grid_constant__ P
 #pragma unroll
         for (int j = 0; j < VEC; ++j) { m1[j] = -INFINITY; m2[j] = -INFINITY; k0[j] = 0; }
 
-        constexpr int U = 8;  // independent 128-bit loads in flight per thread
+        // U independent 128-bit loads in flight per thread
         int k = 0;
         for (; k + U <= P.C; k += U) {
             float v[U][VEC];
 #pragma unroll
             for (int q = 0; q < U; ++q) {
                 if (VEC == 4) {
-                    const float4 t = ldg_stream4(cls + static_cast<size_t>(k + q) * hw);
+                    const float4 t = HINT ? ldg_stream4_256(cls + static_cast<size_t>(k + q) * hw) : ldg_stream4(cls + static_cast<size_t>(k + q) * hw);
                     v[q][0] = t.x; v[q][1 % VEC] = t.y; v[q][2 % VEC] = t.z; v[q][3 % VEC] = t.w;
                 } else {
                     v[q][0] = ldg_stream1(cls + static_cast<size_t>(k + q) * hw);
@@ -802,7 +810,7 @@ static int g_filter_variant = [] {
 }();
 static int g_bulk_ppt = [] {
     const char *v = getenv("YSB_BULK_PPT");
-    return v ? atoi(v) : 4;
+    return v ? atoi(v) : 0;
 }();
 
 cudaError_t launch_filter(const Plan &P, int vec, uint64_t *d_keys, int64_t key_cap, int32_t *d_counts,
@@ -842,10 +850,25 @@ cudaError_t launch_filter(const Plan &P, int vec, uint64_t *d_keys, int64_t key_
         return e;
     } else if (P.layout == LAYOUT_PLANES) {
         const dim3 grid((P.units_per_img + 255) / 256, P.batch);
-        if (vec == 4)
-            k_filter_planes<4><<<grid, 256, 0, stream>>>(P, d_keys, key_cap, d_counts);
-        else
+        const dim3 grid128((P.units_per_img + 127) / 128, P.batch);
+        if (vec != 4) {
             k_filter_planes<1><<<grid, 256, 0, stream>>>(P, d_keys, key_cap, d_counts);
+        } else {
+            switch (g_bulk_ppt) {  // profiling variants of the direct-load kernel
+            case 3: k_filter_planes<4, 4, 256, 6><<<grid, 256, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
+            case 4: k_filter_planes<4, 8, 256, 1, 1><<<grid, 256, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
+            case 5: k_filter_planes<4, 16, 256, 2><<<grid, 256, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
+            case 6: k_filter_planes<4, 8, 128, 8><<<grid128, 128, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
+            case 7: k_filter_planes<4, 10, 256, 3><<<grid, 256, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
+            case 8: k_filter_planes<4, 10, 256, 3, 1><<<grid, 256, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
+            case 9: k_filter_planes<4, 10, 128, 6, 1><<<grid128, 128, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
+            case 10: k_filter_planes<4, 10, 128, 6><<<grid128, 128, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
+            case 11: k_filter_planes<4, 20, 128, 4><<<grid128, 128, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
+            case 1: k_filter_planes<4><<<grid, 256, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
+            // default: 128-thread CTAs, 16 loads of 128 bits in flight per thread, 256-byte L2 prefetch granularity
+            default: k_filter_planes<4, 16, 128, 4, 1><<<grid128, 128, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
+            }
+        }
     } else {
         const size_t smem = static_cast<size_t>(kRowsTile) * (P.row_w_in | 1) * sizeof(float);
         if (smem > 48 * 1024) {

@@ -27,15 +27,35 @@ constexpr int kChunk = 64;
 constexpr int kMaxKeep = YSB_MAX_DET_LIMIT;
 constexpr int kKeyBatch = 8;  // independent 64-bit key loads in flight per thread in the selection passes
 
+// Phase timestamps of image 0..63 (profiling builds only: -DYSB_K2_TIMING), read back by ysb_debug_k2_timing().
+#ifdef YSB_K2_TIMING
+__device__ long long g_k2_timing[64][16];
+#define K2_STAMP(slot) do { if (threadIdx.x == 0 && blockIdx.x < 64) g_k2_timing[blockIdx.x][slot] = clock64(); } while (0)
+#define K2_ACC_BEGIN() k2_t0 = clock64()
+#define K2_ACC(slot) do { const long long k2_t1 = clock64(); k2_acc[slot - 8] += k2_t1 - k2_t0; k2_t0 = k2_t1; } while (0)
+#define K2_ACC_RESET() long long k2_acc[5] = {0, 0, 0, 0, 0}; long long k2_t0 = 0
+#define K2_ACC_FLUSH() do { if (threadIdx.x == 0 && blockIdx.x < 64) for (int q = 0; q < 5; ++q) g_k2_timing[blockIdx.x][8 + q] = k2_acc[q]; } while (0)
+#else
+#define K2_ACC_BEGIN() do { } while (0)
+#define K2_ACC(slot) do { } while (0)
+#define K2_ACC_RESET() do { } while (0)
+#define K2_ACC_FLUSH() do { } while (0)
+#define K2_STAMP(slot) do { } while (0)
+#endif
+
 struct NmsSmem {
     uint64_t keys[kTrancheCap];
     float4 raw[kTrancheCap];
     uint32_t hist[kBins];
-    OffBox kept_box[kMaxKeep];
+    float2 kept_x[kMaxKeep];
+    float2 kept_y[kMaxKeep];
+    float kept_a[kMaxKeep];
     uint64_t kept_key[kMaxKeep];
     float4 kept_raw[kMaxKeep];
     uint8_t kept_flag[kMaxKeep];
-    OffBox chunk_box[kChunk];
+    float2 chunk_x[kChunk];
+    float2 chunk_y[kChunk];
+    float chunk_a[kChunk];
     uint64_t chunk_mask[kChunk];   // row i: later candidates j > i that i suppresses
     unsigned int chunk_pred[kChunk][2];  // row i: earlier candidates j < i that suppress i (lo/hi words)
     float area[kTrancheCap];       // post-filter: areas of the offset boxes
@@ -52,7 +72,7 @@ struct NmsSmem {
 // Arguments of the array flavour (utils.numba_nms / utils.gpu_nms on one explicit box array).
 struct ArrayArgs {
     const float4 *boxes;   // (m) xyxy
-    OffBox *kept_box;      // global workspace (m): the keep list is unbounded here
+    BoxSoA kept;           // global workspace (m boxes): the keep list is unbounded here
     int32_t *keep;         // out: kept indices, visiting order
     int32_t *keep_cnt;     // out
     int iou_kind, cmp;
@@ -60,10 +80,12 @@ struct ArrayArgs {
 };
 
 template <bool ARRAY>
-__device__ __forceinline__ bool pair_hit(const OffBox &a, const OffBox &b, const IouThr &t, const ArrayArgs &aa)
+__device__ __forceinline__ bool pair_hit(const BoxSoA &list, int i, const OffBox &b, const IouThr &t, const ArrayArgs &aa)
 {
-    if (!ARRAY) return iou_reaches<false>(a, b, t);
-    if (aa.iou_kind == YSB_IOU_NUMBA_F64MIX) return aa.cmp == YSB_CMP_GT ? iou_reaches<true>(a, b, t) : iou_reaches<false>(a, b, t);
+    if (!ARRAY) return iou_reaches_staged<false>(list, i, b, t);
+    if (aa.iou_kind == YSB_IOU_NUMBA_F64MIX)
+        return aa.cmp == YSB_CMP_GT ? iou_reaches_staged<true>(list, i, b, t) : iou_reaches_staged<false>(list, i, b, t);
+    const OffBox a = soa_load(list, i);
     const float v = iou_kind_f32(aa.iou_kind, make_float4(a.x1, a.y1, a.x2, a.y2), make_float4(b.x1, b.y1, b.x2, b.y2));
     return aa.cmp == YSB_CMP_GT ? (v > aa.thr32) : (v >= aa.thr32);
 }
@@ -144,25 +166,64 @@ __device__ uint64_t select_lower_bound(NmsSmem &S, const uint64_t *__restrict__ 
     }
 }
 
-// Descending bitonic sort of n2 (power of two, <= kTrancheCap) keys in shared memory.  Strides below 32 pairs are
-// resolved inside a warp's private 64-element window, so only a __syncwarp separates those stages.
-__device__ void bitonic_sort_desc(uint64_t *a, int n2)
+// Descending sort of keys[0..n) (n <= 1024*E) by a bitonic network held in registers: element i = tid + 1024*r lives in
+// register r of thread tid.  Strides >= 1024 are thread-local, strides < 32 use warp shuffles, only strides 32..512 go
+// through shared memory (15 of the 55 stages at n = 1024).  Slots beyond n sort as 0 (smaller than any real key).
+template <int E>
+__device__ void bitonic_sort_desc(uint64_t *keys, int n)
 {
-    const int half = n2 >> 1;
-    for (int k = 2, lk = 1; k <= n2; k <<= 1, ++lk) {
-        for (int j = k >> 1, lj = lk - 1; j > 0; j >>= 1, --lj) {
-            for (int t = threadIdx.x; t < half; t += kThreads) {
-                const int i = ((t >> lj) << (lj + 1)) | (t & (j - 1));
-                const int p = i | j;
-                const bool desc = (i & k) == 0;
-                const uint64_t x = a[i], y = a[p];
-                if ((x < y) == desc) { a[i] = y; a[p] = x; }
-            }
-            // pairs of stride j < 32 handled by thread t touch only elements [64*(t/32), 64*(t/32)+64): warp-private
-            if (j > 32) __syncthreads(); else __syncwarp();
-        }
-        __syncthreads();
+    const int tid = threadIdx.x;
+    constexpr int n2 = kThreads * E;
+    uint64_t v[E];
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const int i = tid + kThreads * r;
+        v[r] = i < n ? keys[i] : 0ull;
     }
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= kThreads) {
+                // thread-local stage: register pairs (0,1),(2,3) for stride 1024, (0,2),(1,3) for stride 2048
+                auto cx = [&](int r0, uint64_t &a, uint64_t &b) {
+                    const bool desc = ((tid + kThreads * r0) & k) == 0;
+                    const uint64_t hi = a > b ? a : b, lo = a > b ? b : a;
+                    a = desc ? hi : lo;
+                    b = desc ? lo : hi;
+                };
+                if (E >= 2 && j == kThreads) {
+                    cx(0, v[0], v[1 % E]);
+                    if (E == 4) cx(2, v[2 % E], v[3 % E]);
+                } else if (E == 4 && j == 2 * kThreads) {
+                    cx(0, v[0], v[2 % E]);
+                    cx(1, v[1 % E], v[3 % E]);
+                }
+            } else if (j >= 32) {
+#pragma unroll
+                for (int r = 0; r < E; ++r) keys[tid + kThreads * r] = v[r];
+                __syncthreads();
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    const int i = tid + kThreads * r;
+                    const uint64_t o = keys[i ^ j];
+                    const bool take_max = ((i & j) == 0) == ((i & k) == 0);
+                    v[r] = take_max ? (v[r] > o ? v[r] : o) : (v[r] > o ? o : v[r]);
+                }
+                __syncthreads();
+            } else {
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    const int i = tid + kThreads * r;
+                    const uint64_t o = __shfl_xor_sync(0xffffffffu, v[r], j);
+                    const bool take_max = ((i & j) == 0) == ((i & k) == 0);
+                    v[r] = take_max ? (v[r] > o ? v[r] : o) : (v[r] > o ? o : v[r]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < E; ++r) keys[tid + kThreads * r] = v[r];
+    __syncthreads();
 }
 
 template <bool ARRAY>
@@ -185,7 +246,8 @@ k_select_nms(const __grid_constant__ Plan P, const uint64_t *__restrict__ keys_a
         }
         return;
     }
-    OffBox *const kept_box = ARRAY ? aa.kept_box : S.kept_box;
+    const BoxSoA kept_box = ARRAY ? aa.kept : BoxSoA{S.kept_x, S.kept_y, S.kept_a};
+    const BoxSoA chunk_box{S.chunk_x, S.chunk_y, S.chunk_a};
     const uint64_t *keys = keys_all + static_cast<int64_t>(img) * key_cap;
     const uint32_t smax = static_cast<uint32_t>(cnt[2]);
     const uint32_t smin = ~static_cast<uint32_t>(cnt[3]);
@@ -199,9 +261,12 @@ k_select_nms(const __grid_constant__ Plan P, const uint64_t *__restrict__ keys_a
     int kept = 0, processed = 0, n_tranche = 0;
     uint64_t hi_incl = ~0ull;
     for (;;) {
+        K2_STAMP(0);
+        K2_ACC_RESET();
         // ---- 1. select the next tranche ------------------------------------------------------------------
         uint64_t lo = 0;
         if (M - processed > kTrancheCap) lo = select_lower_bound(S, keys, M, smin, hi_incl, nbits);
+        K2_STAMP(1);
         if (tid == 0) S.n_sel = 0;
         __syncthreads();
         for (int i0 = 0; i0 < M; i0 += kKeyBatch * kThreads) {
@@ -228,19 +293,20 @@ k_select_nms(const __grid_constant__ Plan P, const uint64_t *__restrict__ keys_a
             }
         }
         __syncthreads();
+        K2_STAMP(2);
         const int n = min(S.n_sel, kTrancheCap);
         n_tranche = n;
         // ---- 2. sort descending, decode boxes -------------------------------------------------------------
-        int n2 = 1;
-        while (n2 < n) n2 <<= 1;
-        for (int i = n + tid; i < n2; i += kThreads) S.keys[i] = 0ull;
-        __syncthreads();
-        bitonic_sort_desc(S.keys, n2);
+        if (n <= kThreads) bitonic_sort_desc<1>(S.keys, n);
+        else if (n <= 2 * kThreads) bitonic_sort_desc<2>(S.keys, n);
+        else bitonic_sort_desc<4>(S.keys, n);
         const int n_use = min(n, limit - processed);
+        K2_STAMP(3);
         int decoded_upto = 0;  // boxes are decoded 1024 at a time, only as far as the NMS walk gets
         // ---- 3. greedy NMS over the tranche, 64 candidates at a time ---------------------------------------
         for (int c0 = 0; c0 < n_use && kept < max_det; c0 += kChunk) {
             const int cn = min(kChunk, n_use - c0);
+            K2_ACC_BEGIN();
             if (c0 + cn > decoded_upto) {
                 const int i = decoded_upto + tid;
                 if (i < n_use) {
@@ -250,6 +316,7 @@ k_select_nms(const __grid_constant__ Plan P, const uint64_t *__restrict__ keys_a
                 decoded_upto = min(n_use, decoded_upto + kThreads);
                 __syncthreads();
             }
+            K2_ACC(8);
             // phase A: 16 threads per candidate test it against the kept list
             {
                 const int j = tid >> 4, sub = tid & 15;
@@ -262,7 +329,7 @@ k_select_nms(const __grid_constant__ Plan P, const uint64_t *__restrict__ keys_a
                     score = key_score(key);
                     const float off = P.class_aware ? __fmul_rn(static_cast<float>(key_cls(key)), 4096.0f) : 0.0f;
                     ob = make_offbox(S.raw[c0 + j], off);
-                    for (int k = sub; k < kept; k += 16) sup |= pair_hit<ARRAY>(kept_box[k], ob, thr, aa);
+                    for (int k = sub; k < kept; k += 16) sup |= pair_hit<ARRAY>(kept_box, k, ob, thr, aa);
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, sup);
                 const unsigned half = (tid & 16) ? 0xffff0000u : 0x0000ffffu;
@@ -271,20 +338,21 @@ k_select_nms(const __grid_constant__ Plan P, const uint64_t *__restrict__ keys_a
                     S.chunk_pred[j][1] = 0u;
                     // a zero score is never picked by "while sum > 0" (utils/nms.py:16): it is neither kept nor a suppressor
                     S.chunk_alive[j] = valid && !(bal & half) && score > 0.0f;
-                    if (valid) S.chunk_box[j] = ob;
+                    if (valid) soa_store(chunk_box, j, ob);
                 }
             }
             __syncthreads();
+            K2_ACC(9);
             // phase B: in-chunk suppression bitmask, mask[i] bit j (j > i) = IoU(i, j) reaches the threshold
             {
                 const int i = tid >> 4, sub = tid & 15;
                 uint32_t lo32 = 0, hi32 = 0;
                 if (i < cn && S.chunk_alive[i]) {
-                    const OffBox bi = S.chunk_box[i];
+                    const OffBox bi = soa_load(chunk_box, i);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const int j = sub * 4 + q;
-                        if (j > i && j < cn && S.chunk_alive[j] && pair_hit<ARRAY>(bi, S.chunk_box[j], thr, aa)) {
+                        const int j = q * 16 + sub;  // lanes walk consecutive boxes: conflict-free shared loads
+                        if (j > i && j < cn && S.chunk_alive[j] && pair_hit<ARRAY>(chunk_box, j, bi, thr, aa)) {
                             if (j < 32) lo32 |= 1u << j; else hi32 |= 1u << (j - 32);
                             atomicOr(&S.chunk_pred[j][i >> 5], 1u << (i & 31));  // rare: suppression inside a chunk
                         }
@@ -296,6 +364,7 @@ k_select_nms(const __grid_constant__ Plan P, const uint64_t *__restrict__ keys_a
                 if (sub == 0) S.chunk_mask[i] = (static_cast<uint64_t>(hi32) << 32) | lo32;
             }
             __syncthreads();
+            K2_ACC(10);
             // phase C: resolve the chunk (warp 0)
             if (tid < 32) {
                 const unsigned a_lo = __ballot_sync(0xffffffffu, S.chunk_alive[tid] != 0);
@@ -334,10 +403,11 @@ k_select_nms(const __grid_constant__ Plan P, const uint64_t *__restrict__ keys_a
                 }
             }
             __syncthreads();
+            K2_ACC(11);
             const uint64_t keep = S.keep_mask;
             if (tid < kChunk && ((keep >> tid) & 1ull)) {
                 const int at = kept + __popcll(keep & ((1ull << tid) - 1ull));
-                kept_box[at] = S.chunk_box[tid];
+                soa_store(kept_box, at, soa_load(chunk_box, tid));
                 if (ARRAY) {
                     aa.keep[at] = static_cast<int32_t>(key_cand(S.keys[c0 + tid]));
                 } else {
@@ -347,12 +417,15 @@ k_select_nms(const __grid_constant__ Plan P, const uint64_t *__restrict__ keys_a
             }
             kept += __popcll(keep);
             __syncthreads();
+            K2_ACC(12);
         }
         if (window) {  // the count filter below needs every survivor's box (single tranche holds them all)
             for (int i = decoded_upto + tid; i < n_use; i += kThreads)
                 S.raw[i] = candidate_xyxy(P, img, static_cast<int>(key_cand(S.keys[i])));
             __syncthreads();
         }
+        K2_STAMP(4);
+        K2_ACC_FLUSH();
         processed += n;
         if (kept >= max_det || processed >= limit || processed >= M) break;
         hi_incl = lo - 1;  // lo > 0 here: keys remain below it
@@ -378,20 +451,21 @@ k_select_nms(const __grid_constant__ Plan P, const uint64_t *__restrict__ keys_a
             }
             __syncthreads();
             for (int r = warp; r < kept; r += kThreads / 32) {
-                const OffBox br = kept_box[r];
+                const OffBox br = soa_load(kept_box, r);
                 int c = 0;
                 for (int j = lane; j < mm; j += 32) {
-                    const float4 o = S.raw[j];
-                    OffBox bj;
-                    bj.x1 = o.x; bj.y1 = o.y; bj.x2 = o.z; bj.y2 = o.w; bj.area = S.area[j];
-                    c += iou_reaches<true>(br, bj, thr) ? 1 : 0;
+                    const float4 o = S.raw[j];  // offset box (x1, y1, x2, y2)
+                    const float dw = __fsub_rn(fminf(br.x2, o.z), fmaxf(br.x1, o.x));
+                    const float dh = __fsub_rn(fminf(br.y2, o.w), fmaxf(br.y1, o.y));
+                    if (thr.positive && !(dw > 0.0f && dh > 0.0f)) continue;
+                    c += iou_decide<true>(dw, dh, br.area, S.area[j], thr) ? 1 : 0;
                 }
                 c = __reduce_add_sync(0xffffffffu, c);
                 if (lane == 0) S.kept_flag[r] = c > 1;
             }
         } else {
         for (int r = warp; r < kept; r += kThreads / 32) {
-            const OffBox br = kept_box[r];
+            const OffBox br = soa_load(kept_box, r);
             int c = 0;
             float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f, ws = 0.f;
             for (int j = lane; j < mm; j += 32) {
@@ -430,6 +504,7 @@ k_select_nms(const __grid_constant__ Plan P, const uint64_t *__restrict__ keys_a
     }
     if (tid == 0) S.out_count = 0;
     __syncthreads();
+    K2_STAMP(5);
     // ---- ordered write of the surviving rows ---------------------------------------------------------------
     {
         const int r = tid;  // kept <= kMaxKeep == kThreads
@@ -457,6 +532,7 @@ k_select_nms(const __grid_constant__ Plan P, const uint64_t *__restrict__ keys_a
             row[5] = static_cast<float>(key_cls(key));
             if (det_idx) det_idx[static_cast<size_t>(img) * max_det + at] = static_cast<int32_t>(key_cand(key));
         }
+        K2_STAMP(6);
         if (tid == kThreads - 1) {
             const int total = before + __popc(bal);
             det_cnt[img] = (total == 0 && P.none_when_empty) ? -1 : total;
@@ -508,7 +584,7 @@ static size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255);
 size_t array_nms_workspace_bytes(int64_t m)
 {
     const size_t mm = static_cast<size_t>(m > 0 ? m : 1);
-    return align256(sizeof(uint64_t) * mm) + align256(sizeof(OffBox) * mm) + align256(sizeof(int32_t) * 4) + 256;
+    return align256(sizeof(uint64_t) * mm) + 3 * align256(sizeof(float2) * mm) + align256(sizeof(int32_t) * 4) + 256;
 }
 
 cudaError_t launch_array_nms(const float *d_boxes, const float *d_scores, int64_t m, double iou_thr, int cmp, int iou_kind,
@@ -518,8 +594,10 @@ cudaError_t launch_array_nms(const float *d_boxes, const float *d_scores, int64_
     const size_t mm = static_cast<size_t>(m);
     uintptr_t base = (reinterpret_cast<uintptr_t>(ws) + 255) & ~static_cast<uintptr_t>(255);
     uint64_t *keys = reinterpret_cast<uint64_t *>(base);
-    OffBox *kept = reinterpret_cast<OffBox *>(base + align256(sizeof(uint64_t) * mm));
-    int32_t *counts = reinterpret_cast<int32_t *>(base + align256(sizeof(uint64_t) * mm) + align256(sizeof(OffBox) * mm));
+    const size_t seg = align256(sizeof(float2) * mm);
+    uintptr_t kb = base + align256(sizeof(uint64_t) * mm);
+    BoxSoA kept{reinterpret_cast<float2 *>(kb), reinterpret_cast<float2 *>(kb + seg), reinterpret_cast<float *>(kb + 2 * seg)};
+    int32_t *counts = reinterpret_cast<int32_t *>(kb + 3 * seg);
     cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int32_t) * 4, stream);
     if (e != cudaSuccess) return e;
     k_array_keys<<<static_cast<unsigned>((m + 255) / 256), 256, 0, stream>>>(d_scores, static_cast<int>(m), keys, counts);
@@ -537,7 +615,7 @@ cudaError_t launch_array_nms(const float *d_boxes, const float *d_scores, int64_
     P.max_det = static_cast<int>((max_keep > 0 && max_keep < m) ? max_keep : m);
     ArrayArgs aa;
     aa.boxes = reinterpret_cast<const float4 *>(d_boxes);
-    aa.kept_box = kept;
+    aa.kept = kept;
     aa.keep = d_keep;
     aa.keep_cnt = d_keep_cnt;
     aa.iou_kind = iou_kind;
@@ -546,5 +624,9 @@ cudaError_t launch_array_nms(const float *d_boxes, const float *d_scores, int64_
     k_select_nms<true><<<1, kThreads, sizeof(NmsSmem), stream>>>(P, keys, m, counts, nullptr, nullptr, nullptr, aa);
     return cudaGetLastError();
 }
+
+#ifdef YSB_K2_TIMING
+cudaError_t debug_k2_timing(long long *host_out) { return cudaMemcpyFromSymbol(host_out, g_k2_timing, sizeof(g_k2_timing)); }
+#endif
 
 }  // namespace ysb
