@@ -24,6 +24,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "post-proc images/s (YOLOv5s 640^2, conf=0.001)"
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
+NCU_TRAFFIC_BYTES = {("yolov5", 640, 64, "dense"): 523926784 + 7163136}
 UNIT = "images/s"
 
 
@@ -337,6 +339,14 @@ def run_ours(args):
     sync_all()
     filt_ms = [e[0].elapsed_time(e[1]) for e in evs]
     nms_ms = [e[2].elapsed_time(e[3]) for e in evs]
+    # the dominant kernel alone (no concurrent NMS kernel), same inputs, same stream, CUDA events around each launch
+    iso = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(50)]
+    for a, b_ in iso:
+        a.record(stream)
+        launch_filter(ptrs, slots[0], stream)
+        b_.record(stream)
+    torch.cuda.synchronize()
+    iso_ms = statistics.mean(a.elapsed_time(b_) for a, b_ in iso)
     m_mean = float(slots[0].counts[:, 0].float().mean().item())
 
     # ---- end-to-end: host (pinned) heads -> H2D -> kernels -> D2H of rows + counts, per step -------------------
@@ -395,7 +405,13 @@ def run_ours(args):
             "gpu_launches": 2 * args.steps,
             "roofline": {"kernel": "k_filter_planes<4> (decode-sigmoid + filter + class pick + compaction)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": None,
+                         "peak_source": peak_src,
+                         "traffic": NCU_TRAFFIC_BYTES.get((args.family, args.img, args.batch, args.dist)),
+                         "traffic_source": "profiles/r1_filter_ncu_raw.txt (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture)",
+                         "launch_ms_alone": iso_ms, "achieved_alone": algo_bytes / (iso_ms * 1e-3) / 1e9,
+                         "frac_alone": algo_bytes / (iso_ms * 1e-3) / 1e9 / peak,
+                         "note": "achieved/frac use the launch duration inside the timed (pipelined) region, where the NMS "
+                                 "kernel of the previous batch runs concurrently; *_alone is the same kernel timed without it",
                          "algorithmic_bytes_per_launch": algo_bytes,
                          "bytes_per_image": f"N*(C+1)*4 read + M*8 written = {N * n_read_ch * 4} + {m_mean * 8:.0f}",
                          "launch_ms": filt_mean_ms},
