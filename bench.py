@@ -58,9 +58,12 @@ def workload_config(args, world):
     }
 
 
-def bench_hyp():
+def bench_hyp(family="yolov5"):
     import oracle
-    return oracle.default_hyp(num_class=80)
+    hyp = oracle.default_hyp(num_class=80)
+    if family == "fcos":  # config/train_fcos.yaml:110-116
+        hyp.update(cls_threshold=0.2, iou_threshold=0.35, max_predictions_per_img=100)
+    return hyp
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -218,7 +221,7 @@ def run_ours(args):
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
-    hyp = bench_hyp()
+    hyp = bench_hyp(args.family)
     heads = synth.make_heads(args.family, args.batch, args.img, args.img, 80, args.dist, 1234 + rank, dev)
     anchors = torch.tensor(synth.V5_ANCHORS_PX) if args.family in ("yolov5", "yolov7") else None
     pp = PostProcessor(args.family, hyp, anchors=anchors)
@@ -389,7 +392,9 @@ def run_ours(args):
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         C = 80
-        n_read_ch = C + 1                      # class planes + objectness; box planes are not read by K1
+        # channels the filter kernel must read per candidate: class logits (+ objectness / centerness / conf when the
+        # family has one); box channels are not read by it
+        n_read_ch = C + (0 if args.family in ("yolov8", "retinanet") else 1)
         algo_bytes = args.batch * (N * n_read_ch * 4 + m_mean * 8)
         filt_mean_ms = statistics.mean(filt_ms)
         achieved = algo_bytes / (filt_mean_ms * 1e-3) / 1e9
@@ -403,7 +408,8 @@ def run_ours(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "host pinned head tensors -> ysb_filter_candidates + ysb_select_nms -> host rows/counts"},
             "gpu_launches": 2 * args.steps,
-            "roofline": {"kernel": "k_filter_planes<4> (decode-sigmoid + filter + class pick + compaction)",
+            "roofline": {"kernel": ("k_filter_rows" if args.family in ("yolov7", "retinanet", "retinanet_exp") else "k_filter_planes<4>")
+                                   + " (decode-sigmoid + filter + class pick + compaction)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src,
                          "traffic": NCU_TRAFFIC_BYTES.get((args.family, args.img, args.batch, args.dist)),
@@ -413,14 +419,14 @@ def run_ours(args):
                          "note": "achieved/frac use the launch duration inside the timed (pipelined) region, where the NMS "
                                  "kernel of the previous batch runs concurrently; *_alone is the same kernel timed without it",
                          "algorithmic_bytes_per_launch": algo_bytes,
-                         "bytes_per_image": f"N*(C+1)*4 read + M*8 written = {N * n_read_ch * 4} + {m_mean * 8:.0f}",
+                         "bytes_per_image": f"N*{n_read_ch}*4 read + M*8 written = {N * n_read_ch * 4} + {m_mean * 8:.0f}",
                          "launch_ms": filt_mean_ms},
             "pipeline": bool(args.pipeline),
             "stages_ms": {"filter_compact": filt_mean_ms, "select_sort_nms": statistics.mean(nms_ms),
                           "filter_p50": statistics.median(filt_ms), "nms_p50": statistics.median(nms_ms)},
             "survivors_per_image": m_mean,
         }
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and args.family == "yolov5":
             v, dt = cpu_images_per_second(cpu_heads(args.cpu_images, args), 1)
             line["cpu_baseline"] = {
                 "value": v, "unit": UNIT, "cores": 1, "kind": "port",

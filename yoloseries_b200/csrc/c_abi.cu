@@ -163,16 +163,17 @@ static int build_plan(const ysb_params *p, const void *const *d_heads, int num_h
     out->heads_expected = expected_heads(p);
     out->vec = 1;
     if (P.layout == LAYOUT_PLANES) {
-        bool v4 = true;
-        for (int l = 0; l < L; ++l) v4 = v4 && (P.lv[l].hw % 4 == 0);
+        bool aligned = true;
         if (d_heads)
-            for (int i = 0; i < num_heads; ++i) v4 = v4 && ((reinterpret_cast<uintptr_t>(d_heads[i]) & 15u) == 0);
-        out->vec = v4 ? 4 : 1;
-        int units = 0;
+            for (int i = 0; i < num_heads; ++i) aligned = aligned && ((reinterpret_cast<uintptr_t>(d_heads[i]) & 15u) == 0);
+        int n4 = 0, units = 0;
         for (int l = 0; l < L; ++l) {
+            P.lv[l].vec = (aligned && P.lv[l].hw % 4 == 0) ? 4 : 1;  // e.g. FCOS' 5x5 level falls back to scalar units
+            n4 += P.lv[l].vec == 4;
             P.lv[l].unit_off = units;
-            units += A * (P.lv[l].hw / out->vec);
+            units += A * (P.lv[l].hw / P.lv[l].vec);
         }
+        out->vec = n4 == L ? 4 : (n4 > 0 ? 3 : 1);  // 4: all levels vectorised, 3: mixed, 1: none
         P.units_per_img = units;
     } else if (p->input_kind == YSB_INPUT_DECODED_ROWS) {
         P.L = 1;

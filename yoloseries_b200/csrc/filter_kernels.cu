@@ -171,10 +171,12 @@ __global__ void __launch_bounds__(THREADS, MINB) k_filter_planes(const __grid_co
         for (int i = 1; i < YSB_MAX_LEVELS; ++i)
             if (i < P.L && u >= P.lv[i].unit_off) l = i;
         const LevelDesc &lv = P.lv[l];
-        const int upa = lv.hw / VEC;  // units per anchor
+        const bool vec4 = VEC == 4 && lv.vec == 4;  // levels whose planes are not 16-byte sized use one position per unit
+        const int upos = vec4 ? 4 : 1;
+        const int upa = lv.hw / upos;  // units per anchor
         const int ru = u - lv.unit_off;
         const int a = ru / upa;
-        const int pos = (ru - a * upa) * VEC;
+        const int pos = (ru - a * upa) * upos;
         const int cand0 = lv.cand_off + a * lv.hw + pos;
         const size_t hw = static_cast<size_t>(lv.hw);
         const float *cls = lv.p0 + (static_cast<size_t>(img * P.A + a) * P.cls_nch + P.cls_ch) * hw + pos;
@@ -190,11 +192,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_filter_planes(const __grid_co
             float v[U][VEC];
 #pragma unroll
             for (int q = 0; q < U; ++q) {
-                if (VEC == 4) {
+                if (vec4) {
                     const float4 t = HINT ? ldg_stream4_256(cls + static_cast<size_t>(k + q) * hw) : ldg_stream4(cls + static_cast<size_t>(k + q) * hw);
                     v[q][0] = t.x; v[q][1 % VEC] = t.y; v[q][2 % VEC] = t.z; v[q][3 % VEC] = t.w;
                 } else {
                     v[q][0] = ldg_stream1(cls + static_cast<size_t>(k + q) * hw);
+#pragma unroll
+                    for (int j = 1; j < VEC; ++j) v[q][j] = -INFINITY;
                 }
             }
 #pragma unroll
@@ -204,11 +208,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_filter_planes(const __grid_co
         }
         for (; k < P.C; ++k) {
             float v[VEC];
-            if (VEC == 4) {
+            if (vec4) {
                 const float4 t = ldg_stream4(cls + static_cast<size_t>(k) * hw);
                 v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w;
             } else {
                 v[0] = ldg_stream1(cls + static_cast<size_t>(k) * hw);
+#pragma unroll
+                for (int j = 1; j < VEC; ++j) v[j] = -INFINITY;
             }
 #pragma unroll
             for (int j = 0; j < VEC; ++j) top2_update(v[j], k, m1[j], m2[j], k0[j]);
@@ -219,7 +225,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_filter_planes(const __grid_co
         if (P.use_obj) {
             const float *ob = (P.obj_src == 2 ? lv.p2 : lv.p0) +
                               (static_cast<size_t>(img * P.A + a) * P.obj_nch + P.obj_ch) * hw + pos;
-            if (VEC == 4) {
+            if (vec4) {
                 const float4 t = ldg_stream4(ob);
                 objv[0] = t.x; objv[1 % VEC] = t.y; objv[2 % VEC] = t.z; objv[3 % VEC] = t.w;
             } else {
@@ -228,6 +234,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_filter_planes(const __grid_co
         }
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
+            if (j >= upos) break;
             float score;
             int c;
             bool pre;
@@ -712,9 +719,9 @@ static cudaError_t launch_async(const Plan &P, int num_sms, uint64_t *d_keys, in
 
 // -------------------------------------------------------------------------------------------------------
 // rows layout (channels-last heads: YOLOv7, RetinaNet cls; and the decoded (b, N, C') tensor of any family).
-// A CTA stages a tile of whole rows in shared memory with coalesced 128-bit loads (rows are 340 B / 320 B and
-// only 4-byte aligned individually, the tile is contiguous), then one thread scans one row.  The shared row
-// stride is forced odd so that the 32 rows a warp scans sit in 32 different banks.
+// A CTA stages a tile of 128 whole rows in shared memory with cp.async (rows are 340 B / 320 B and only 4-byte
+// aligned individually, but the tile is contiguous and 16-byte aligned), then one thread scans one row; rows with an
+// even float stride are walked with a per-thread rotation so that the 32 rows a warp scans sit in 32 different banks.
 // -------------------------------------------------------------------------------------------------------
 constexpr int kRowsTile = 128;
 
@@ -733,26 +740,19 @@ __global__ void __launch_bounds__(kRowsTile) k_filter_rows(const __grid_constant
     const int r0 = (t - lv.unit_off) * kRowsTile;
     const int nrows = min(kRowsTile, rows_l - r0);
     const int rw = P.row_w_in;
-    const int sstride = rw | 1;
     const float *src = lv.p0 + (static_cast<size_t>(img) * lv.img_rows + r0) * rw;
     const int nfl = nrows * rw;
-    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+    // 16-byte aligned tiles (every reference layout): cp.async straight into a DENSE shared tile -- no register
+    // staging, no per-element address math.  Rows with an even float stride are scanned with a per-thread rotation
+    // (below) instead of padding.  Odd shapes: scalar loads into a tile padded to an odd stride.
+    const bool dense = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && ((nfl & 3) == 0);
+    const int sstride = dense ? rw : (rw | 1);
+    if (dense) {
+        const uint32_t dst = smem_u32(tile);
         const int nv = nfl >> 2;
-        for (int i = threadIdx.x; i < nv; i += kRowsTile) {
-            const float4 v = ldg_stream4(src + 4 * i);
-            int e = 4 * i;
-            int row = e / rw, col = e - row * rw;
-            const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                tile[row * sstride + col] = vv[j];
-                if (++col == rw) { col = 0; ++row; }
-            }
-        }
-        for (int e = (nv << 2) + threadIdx.x; e < nfl; e += kRowsTile) {
-            const int row = e / rw, col = e - row * rw;
-            tile[row * sstride + col] = ldg_stream1(src + e);
-        }
+        for (int i = threadIdx.x; i < nv; i += kRowsTile) cp_async16(dst + 16u * i, src + 4 * i);
+        cp_async_commit();
+        cp_async_wait<0>();
     } else {
         for (int e = threadIdx.x; e < nfl; e += kRowsTile) {
             const int row = e / rw, col = e - row * rw;
@@ -770,8 +770,15 @@ __global__ void __launch_bounds__(kRowsTile) k_filter_rows(const __grid_constant
         const float *cls = row + P.cls_col_in;
         float m1 = -INFINITY, m2 = -INFINITY;
         int k0 = 0;
+        // thread t reads word sstride*t + k: conflict-free when sstride is odd; otherwise start the walk at column t so
+        // that the 32 lanes hit (sstride+1)*t + k.  The visiting order is irrelevant: a unique maximum has a unique
+        // index, and equal maxima force m2 == m1, i.e. the literal path, which walks in index order.
+        int k = (sstride & 1) ? 0 : static_cast<int>(threadIdx.x) % P.C;
 #pragma unroll 8
-        for (int k = 0; k < P.C; ++k) top2_update(cls[k], k, m1, m2, k0);
+        for (int t = 0; t < P.C; ++t) {
+            top2_update(cls[k], k, m1, m2, k0);
+            if (++k == P.C) k = 0;
+        }
         const int cand = lv.cand_off + r0 + threadIdx.x;
         float objv = 0.0f;
         if (P.use_obj) {
@@ -819,7 +826,7 @@ cudaError_t launch_filter(const Plan &P, int vec, uint64_t *d_keys, int64_t key_
     cudaError_t e = cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * 4 * static_cast<size_t>(P.batch), stream);
     if (e != cudaSuccess) return e;
     if (P.batch == 0 || P.N == 0) return cudaSuccess;
-    if (P.layout == LAYOUT_PLANES && vec == 4 && g_filter_variant != 1) {
+    if (P.layout == LAYOUT_PLANES && vec == 4 && g_filter_variant != 1) {  // ring variants need every level vectorised
         static int num_sms = 0;
         if (num_sms == 0) {
             int dev = 0;
@@ -851,7 +858,7 @@ cudaError_t launch_filter(const Plan &P, int vec, uint64_t *d_keys, int64_t key_
     } else if (P.layout == LAYOUT_PLANES) {
         const dim3 grid((P.units_per_img + 255) / 256, P.batch);
         const dim3 grid128((P.units_per_img + 127) / 128, P.batch);
-        if (vec != 4) {
+        if (vec == 1) {
             k_filter_planes<1><<<grid, 256, 0, stream>>>(P, d_keys, key_cap, d_counts);
         } else {
             switch (g_bulk_ppt) {  // profiling variants of the direct-load kernel

@@ -308,12 +308,28 @@ k_select_nms(const __grid_constant__ Plan P, const uint64_t *__restrict__ keys_a
             const int cn = min(kChunk, n_use - c0);
             K2_ACC_BEGIN();
             if (c0 + cn > decoded_upto) {
-                const int i = decoded_upto + tid;
-                if (i < n_use) {
-                    const int cand = static_cast<int>(key_cand(S.keys[i]));
-                    S.raw[i] = ARRAY ? __ldg(aa.boxes + cand) : candidate_xyxy(P, img, cand);
+                if (!ARRAY && P.family == YSB_YOLOV8 && P.input_kind == YSB_INPUT_RAW_HEADS) {
+                    // the DFL decode is 64 loads + 32 exp per box: four threads per candidate (one per side), 256 per round
+                    const int i = decoded_upto + (tid >> 2), side = tid & 3;
+                    float sv = 0.0f;
+                    int cand = 0;
+                    if (i < n_use) {
+                        cand = static_cast<int>(key_cand(S.keys[i]));
+                        sv = v8_side_value(P, img, cand, side);
+                    }
+                    const unsigned qb = (tid & 31) & ~3u;
+                    const float s0 = __shfl_sync(0xffffffffu, sv, qb), s1 = __shfl_sync(0xffffffffu, sv, qb + 1);
+                    const float s2 = __shfl_sync(0xffffffffu, sv, qb + 2), s3 = __shfl_sync(0xffffffffu, sv, qb + 3);
+                    if (side == 0 && i < n_use) S.raw[i] = v8_box_from_sides(P, cand, s0, s1, s2, s3);
+                    decoded_upto = min(n_use, decoded_upto + kThreads / 4);
+                } else {
+                    const int i = decoded_upto + tid;
+                    if (i < n_use) {
+                        const int cand = static_cast<int>(key_cand(S.keys[i]));
+                        S.raw[i] = ARRAY ? __ldg(aa.boxes + cand) : candidate_xyxy(P, img, cand);
+                    }
+                    decoded_upto = min(n_use, decoded_upto + kThreads);
                 }
-                decoded_upto = min(n_use, decoded_upto + kThreads);
                 __syncthreads();
             }
             K2_ACC(8);
