@@ -1,0 +1,157 @@
+"""Edge cases of the CUDA path against the oracle: empty / ragged batches, ties, saturation, degenerate boxes, limits,
+non-square inputs, and size-independent properties at the full BASELINE sizes."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _pp(family, hyp, anchors=True):
+    from yoloseries_b200 import synth
+    from yoloseries_b200.engine import PostProcessor
+    a = torch.tensor(synth.V5_ANCHORS_PX) if (anchors and family in ("yolov5", "yolov7")) else None
+    return PostProcessor(family, hyp, anchors=a)
+
+
+def _check_against_oracle(family, heads, img_h, img_w, hyp):
+    pp = _pp(family, hyp)
+    decoded = pp.decode(heads, img_h, img_w).cpu().numpy()
+    want = oracle.evaluator_nms(family, decoded, hyp)
+    rows, idx = pp.to_list(pp.run(heads, img_h, img_w), as_numpy=True, with_index=True)
+    assert len(rows) == len(want)
+    for i, w in enumerate(want):
+        if w.rows is None:
+            assert rows[i] is None, f"image {i}: expected None"
+            continue
+        assert rows[i] is not None, f"image {i}: unexpected None"
+        np.testing.assert_array_equal(rows[i], w.rows)
+        np.testing.assert_array_equal(idx[i], w.cand_index)
+    return rows, want
+
+
+def test_ragged_batch_with_empty_images():
+    """Images without any survivor give None; neighbours in the same batch are unaffected."""
+    from yoloseries_b200 import synth
+    hyp = oracle.default_hyp()
+    heads = synth.make_heads("yolov5", 5, 320, 320, 80, "crowd", seed=3, device="cuda")
+    for h in heads:                       # images 1 and 3: objectness far below conf_threshold everywhere
+        h.view(5, 3, 85, h.shape[2], h.shape[3])[[1, 3], :, 4] = -30.0
+    rows, want = _check_against_oracle("yolov5", heads, 320, 320, hyp)
+    assert rows[1] is None and rows[3] is None and rows[0] is not None and len(rows[0]) > 0
+
+
+def test_single_survivor_and_empty_after_count_filter():
+    from yoloseries_b200 import synth
+    hyp = oracle.default_hyp()
+    heads = synth.make_heads("yolov5", 2, 128, 128, 80, "dense", seed=4, device="cuda")
+    for h in heads:
+        h.view(2, 3, 85, h.shape[2], h.shape[3])[:, :, 4] = -30.0
+    heads[0].view(2, 3, 85, 16, 16)[0, 1, 4, 5, 7] = 4.0            # exactly one candidate of image 0 survives
+    heads[1].view(2, 3, 85, 8, 8)[1, 0, 4, 2, 2] = 4.0              # image 1: two isolated survivors -> count filter
+    heads[1].view(2, 3, 85, 8, 8)[1, 2, 4, 6, 6] = 4.0              #          leaves an empty (0, 6) array, not None
+    rows, want = _check_against_oracle("yolov5", heads, 128, 128, hyp)
+    assert rows[0].shape == (1, 6)                                    # M == 1: postprocess_bbox window not entered
+    assert rows[1] is not None and rows[1].shape == (0, 6)
+
+
+@pytest.mark.parametrize("value", [0.0, 50.0, -3.0])
+def test_all_equal_logits_tie_breaking(value):
+    """Every candidate has the same score: order is by candidate index, class ties resolve to class 0."""
+    hyp = oracle.default_hyp(postprocess_bbox=False)
+    heads = [torch.full((1, 255, s, s), value, device="cuda") for s in (16, 8, 4)]
+    rows, want = _check_against_oracle("yolov5", heads, 128, 128, hyp)
+    if rows[0] is not None and len(rows[0]):
+        assert np.all(rows[0][:, 5] == 0.0)
+
+
+def test_saturated_and_denormal_logits():
+    from yoloseries_b200 import synth
+    hyp = oracle.default_hyp()
+    heads = synth.make_heads("yolov5", 2, 128, 128, 80, "dense", seed=6, device="cuda")
+    for h in heads:
+        h.mul_(30.0)                      # sigmoid saturates to exactly 1.0 / underflows to denormals and 0
+    _check_against_oracle("yolov5", heads, 128, 128, hyp)
+
+
+@pytest.mark.parametrize("family,h,w", [("yolov5", 384, 640), ("yolov7", 256, 448), ("yolox", 320, 192)])
+def test_non_square_inputs(family, h, w):
+    from yoloseries_b200 import synth
+    hyp = oracle.default_hyp(num_class=12)
+    heads = synth.make_heads(family, 2, h, w, 12, "dense", seed=8, device="cuda")
+    pp = _pp(family, hyp)
+    decoded = pp.decode(heads, h, w).cpu().numpy()
+    hn = [t.cpu().numpy() for t in heads]
+    ref = {"yolov5": lambda: oracle.decode_yolov5(hn, num_class=12), "yolov7": lambda: oracle.decode_yolov7(hn, num_class=12),
+           "yolox": lambda: oracle.decode_yolox(hn, h, num_class=12)}[family]()
+    assert np.all(np.abs(decoded - ref) <= 1e-5 * np.maximum(np.abs(ref), 1.0))
+    _check_against_oracle(family, heads, h, w, hyp)
+
+
+@pytest.mark.parametrize("max_det", [1, 7, 1024])
+def test_max_det_limits(max_det):
+    from yoloseries_b200 import synth
+    hyp = oracle.default_hyp(max_predictions_per_img=max_det, postprocess_bbox=False)
+    heads = synth.make_heads("yolov5", 1, 320, 320, 80, "dense", seed=9, device="cuda")
+    rows, _ = _check_against_oracle("yolov5", heads, 320, 320, hyp)
+    assert len(rows[0]) == max_det
+
+
+def test_limits_raise():
+    from yoloseries_b200 import synth
+    heads = synth.make_heads("yolov5", 1, 64, 64, 80, "dense", seed=1, device="cuda")
+    with pytest.raises(ValueError):
+        _pp("yolov5", oracle.default_hyp(max_predictions_per_img=5000)).run(heads, 64, 64)
+    with pytest.raises(NotImplementedError):
+        _pp("yolov5", oracle.default_hyp(mutil_label=True)).run(heads, 64, 64)
+    with pytest.raises(ValueError):
+        _pp("yolov5", oracle.default_hyp()).run([h.double() for h in heads], 64, 64)
+
+
+def test_class_agnostic_mode_and_deploy_thresholds():
+    from yoloseries_b200 import synth
+    heads = synth.make_heads("yolov5", 2, 320, 320, 80, "crowd", seed=10, device="cuda")
+    _check_against_oracle("yolov5", heads, 320, 320, oracle.default_hyp(agnostic=False))
+    _check_against_oracle("yolov5", heads, 320, 320, oracle.default_hyp(conf_threshold=0.3, cls_threshold=0.3, iou_threshold=0.2))
+
+
+def test_degenerate_and_duplicate_boxes_in_array_nms():
+    from yoloseries_b200.utils import numba_nms
+    rng = np.random.default_rng(5)
+    base = rng.uniform(0, 50, size=(40, 2)).astype(np.float32)
+    boxes = np.concatenate((base, base + rng.uniform(0, 20, size=(40, 2)).astype(np.float32)), axis=1)
+    boxes[5] = [7, 7, 7, 7]                 # zero area: self-IoU is NaN, never suppresses, is kept if scored
+    boxes[6] = [9, 3, 9, 12]                # zero width
+    boxes[10] = boxes[11]                   # exact duplicates: IoU == 1 >= thr
+    boxes[20] = [30, 30, 10, 10]            # inverted box: negative sides
+    scores = rng.uniform(0.1, 1.0, size=40).astype(np.float32)
+    scores[12] = scores[13]                 # equal scores: lower index first
+    for thr in (0.3, 0.5, 1.0):
+        assert numba_nms(boxes, scores, thr) == oracle.numba_nms(boxes, scores, thr)
+
+
+@pytest.mark.parametrize("family,img,batch,dist", [("yolov5", 640, 8, "dense"), ("yolov5", 640, 8, "crowd"),
+                                                   ("yolox", 640, 16, "dense"), ("retinanet", 640, 2, "dense")])
+def test_full_size_properties(family, img, batch, dist):
+    """Size-independent properties on BASELINE-sized inputs (no oracle needed): rows sorted by score, unique candidate
+    indices, counts within max_det, kept boxes of one class never overlap at or above the threshold, and the run is
+    deterministic."""
+    from yoloseries_b200 import synth
+    hyp = oracle.default_hyp(postprocess_bbox=False)
+    heads = synth.make_heads(family, batch, img, img, 80, dist, seed=21, device="cuda")
+    pp = _pp(family, hyp)
+    out = pp.run(heads, img, img)
+    rows, idx = pp.to_list(out, as_numpy=True, with_index=True)
+    rows2, idx2 = pp.to_list(pp.run(heads, img, img), as_numpy=True, with_index=True)
+    for r, i, r2, i2 in zip(rows, idx, rows2, idx2):
+        assert r is not None and 0 < len(r) <= 300
+        np.testing.assert_array_equal(r, r2)
+        np.testing.assert_array_equal(i, i2)
+        assert np.all(np.diff(r[:, 4]) <= 0)
+        assert len(np.unique(i)) == len(i)
+        off = (r[:, :4] + (r[:, 5] * np.float32(4096))[:, None]).astype(np.float32)
+        iou = oracle.numba_iou(off, off)
+        np.fill_diagonal(iou, 0.0)
+        assert not np.any(iou >= hyp["iou_threshold"])
