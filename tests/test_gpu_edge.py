@@ -155,3 +155,9 @@ def test_full_size_properties(family, img, batch, dist):
         iou = oracle.numba_iou(off, off)
         np.fill_diagonal(iou, 0.0)
         assert not np.any(iou >= hyp["iou_threshold"])
+
+
+def test_empty_batch_returns_empty_list():
+    pp = _pp("yolov5", oracle.default_hyp())
+    heads = [torch.zeros((0, 255, s, s), device="cuda") for s in (8, 4, 2)]
+    assert pp.to_list(pp.run(heads, 64, 64)) == []

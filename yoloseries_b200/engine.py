@@ -205,6 +205,8 @@ class PostProcessor:
         """Whole path on the device.  Returns DetectionBuffers (views into reused storage)."""
         flat = [heads] if decoded else flatten_heads(self.family, heads)
         batch = flat[0].shape[0]
+        if batch == 0:  # the reference loops over zero images and returns []
+            return DetectionBuffers(0, int(self.hyp["max_predictions_per_img"]), flat[0].device)
         kind = _lib.INPUT_DECODED_ROWS if decoded else _lib.INPUT_RAW_HEADS
         ent = self._prepare(flat, batch, img_h, img_w, kind)
         if decoded and (flat[0].dim() != 3 or flat[0].shape[2] != ent["row_w"]):
