@@ -136,8 +136,10 @@ __device__ __forceinline__ void emit_keys(const uint64_t (&k)[VEC], unsigned okm
     int base = 0;
     if (lane == 0) {
         base = atomicAdd(cnt, total);
-        atomicMax(reinterpret_cast<unsigned int *>(cnt + 2), wmax);
-        atomicMax(reinterpret_cast<unsigned int *>(cnt + 3), wmin);
+        // the running extrema rarely change after the first warps of an image: look before touching them
+        volatile unsigned int *ext = reinterpret_cast<volatile unsigned int *>(cnt + 2);
+        if (wmax > ext[0]) atomicMax(reinterpret_cast<unsigned int *>(cnt + 2), wmax);
+        if (wmin > ext[1]) atomicMax(reinterpret_cast<unsigned int *>(cnt + 3), wmin);
     }
     base = __shfl_sync(0xffffffffu, base, 0);
     const int64_t at = static_cast<int64_t>(base) + (incl - nk);
@@ -156,8 +158,11 @@ template <int VEC, int U = 8, int THREADS = 256, int MINB = 1, int HINT = 0>
 __global__ void __launch_bounds__(THREADS, MINB) k_filter_planes(const __grid_constant__ Plan P, uint64_t *__restrict__ keys,
                                                                  int64_t key_cap, int32_t *__restrict__ counts)
 {
-    const int img = blockIdx.y;
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    // blockIdx.x = image: CTAs that run at the same time append to DIFFERENT images' counters (the per-image
+    // atomicAdd is the only contended address of the kernel)
+    const bool img_fast = gridDim.x == static_cast<unsigned>(P.batch) && gridDim.y != static_cast<unsigned>(P.batch);
+    const int img = img_fast ? blockIdx.x : blockIdx.y;
+    const int u = (img_fast ? blockIdx.y : blockIdx.x) * blockDim.x + threadIdx.x;
     const bool active = u < P.units_per_img;
     uint64_t out[VEC];
     unsigned okm = 0u;
@@ -729,8 +734,8 @@ __global__ void __launch_bounds__(kRowsTile) k_filter_rows(const __grid_constant
                                                            int64_t key_cap, int32_t *__restrict__ counts)
 {
     extern __shared__ float tile[];
-    const int img = blockIdx.y;
-    const int t = blockIdx.x;
+    const int img = blockIdx.x;  // image fastest: see k_filter_planes
+    const int t = blockIdx.y;
     int l = 0;
 #pragma unroll
     for (int i = 1; i < YSB_MAX_LEVELS; ++i)
@@ -856,8 +861,9 @@ cudaError_t launch_filter(const Plan &P, int vec, uint64_t *d_keys, int64_t key_
         }
         return e;
     } else if (P.layout == LAYOUT_PLANES) {
-        const dim3 grid((P.units_per_img + 255) / 256, P.batch);
-        const dim3 grid128((P.units_per_img + 127) / 128, P.batch);
+        static const bool img_fast = getenv("YSB_IMG_FAST") ? atoi(getenv("YSB_IMG_FAST")) != 0 : true;
+        const dim3 grid = img_fast ? dim3(P.batch, (P.units_per_img + 255) / 256) : dim3((P.units_per_img + 255) / 256, P.batch);
+        const dim3 grid128 = img_fast ? dim3(P.batch, (P.units_per_img + 127) / 128) : dim3((P.units_per_img + 127) / 128, P.batch);
         if (vec == 1) {
             k_filter_planes<1><<<grid, 256, 0, stream>>>(P, d_keys, key_cap, d_counts);
         } else {
@@ -882,7 +888,7 @@ cudaError_t launch_filter(const Plan &P, int vec, uint64_t *d_keys, int64_t key_
             e = cudaFuncSetAttribute(k_filter_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
             if (e != cudaSuccess) return e;
         }
-        const dim3 grid(P.units_per_img, P.batch);
+        const dim3 grid(P.batch, P.units_per_img);
         k_filter_rows<<<grid, kRowsTile, smem, stream>>>(P, d_keys, key_cap, d_counts);
     }
     return cudaGetLastError();
