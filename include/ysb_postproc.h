@@ -45,7 +45,8 @@ extern "C" {
 typedef enum ysb_status {
     YSB_OK = 0,
     YSB_ERR_BAD_ARG = -1,          /* null pointer, negative size, unknown enum value */
-    YSB_ERR_UNSUPPORTED = -2,      /* valid request this build does not implement (e.g. multi_label) */
+    YSB_ERR_UNSUPPORTED = -2,      /* valid request this build does not implement (multi_label for RetinaNet, where the
+                                      reference's own branch is broken) */
     YSB_ERR_WORKSPACE = -3,        /* workspace smaller than *_workspace_bytes() */
     YSB_ERR_CUDA = -4,             /* a CUDA call failed; see ysb_last_cuda_error() */
     YSB_ERR_LIMIT = -5             /* N, num_classes or max_det beyond the limits above */
@@ -103,7 +104,7 @@ typedef struct ysb_params {
     double iou_thr;            /* iou_threshold, compared in float64 (utils/nms.py:22) */
     int32_t max_det;           /* max_predictions_per_img */
     int32_t class_aware;       /* hyp['agnostic'] (sic): add cls*4096 to the boxes before NMS */
-    int32_t multi_label;       /* hyp['mutil_label'] (sic) */
+    int32_t multi_label;       /* hyp['mutil_label'] (sic): one record per (candidate, class) above cls_thr */
     int32_t postprocess_bbox;  /* hyp['postprocess_bbox'] */
     float min_box_wh;          /* min_prediction_box_wh (v7 / FCOS remove_small_boxes) */
     int32_t pre_nms_topk;      /* FCOS pre_nms_topk */

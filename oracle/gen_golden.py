@@ -141,7 +141,8 @@ def utils_case(utils):
 def main():
     utils, trainer = refharness.import_reference()
     os.makedirs(OUT, exist_ok=True)
-    np.savez_compressed(os.path.join(OUT, "utils_nms_iou.npz"), **utils_case(utils))
+    if len(sys.argv) <= 1:
+        np.savez_compressed(os.path.join(OUT, "utils_nms_iou.npz"), **utils_case(utils))
     fcos_thr = {"compute_metric_cls_threshold": 0.2, "compute_metric_iou_threshold": 0.35, "max_predictions_per_img": 100}
     cases = [
         # name, family, dist, img, batch, seed, C, hyp overrides.  Few classes on the small images so that
@@ -165,8 +166,18 @@ def main():
         ("retinanet_exp_dense", "retinanet_exp", "dense", 64, 1, 53, 4, {}),
         ("fcos_dense", "fcos", "dense", 128, 2, 61, 4, fcos_thr),
         ("fcos_sparse", "fcos", "sparse", 256, 1, 62, 6, dict(fcos_thr, compute_metric_cls_threshold=0.05)),
+        # mutil_label: one record per (candidate, class) above the class threshold (eval_yolov5.py:276-279)
+        ("yolov5_multilabel", "yolov5", "crowd", 128, 2, 71, 6, {"mutil_label": True, "compute_metric_cls_threshold": 0.05}),
+        ("yolov5_multilabel_dense", "yolov5", "dense", 64, 1, 72, 4, {"mutil_label": True, "compute_metric_cls_threshold": 0.2}),
+        ("yolov7_multilabel", "yolov7", "crowd", 128, 1, 73, 6, {"mutil_label": True, "compute_metric_cls_threshold": 0.05}),
+        ("yolox_multilabel", "yolox", "dense", 64, 2, 74, 4, {"mutil_label": True, "compute_metric_cls_threshold": 0.3}),
+        ("yolov8_multilabel", "yolov8", "dense", 64, 1, 75, 4, {"mutil_label": True, "compute_metric_cls_threshold": 0.5}),
+        ("fcos_multilabel", "fcos", "dense", 128, 1, 76, 4, dict(fcos_thr, mutil_label=True)),
     ]
+    only = set(sys.argv[1:])
     for name, family, dist, img, batch, seed, C, over in cases:
+        if only and name not in only:
+            continue
         store = evaluator_case(trainer, family, dist, img, batch, seed, C, **over)
         path = os.path.join(OUT, f"{name}.npz")
         np.savez_compressed(path, **store)

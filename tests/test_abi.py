@@ -95,8 +95,15 @@ def test_argument_validation(lib):
     assert lib.ysb_num_candidates(ctypes.byref(p), ctypes.byref(n), None) == _lib.YSB_ERR_BAD_ARG
     p = _v5_params(max_predictions_per_img=5000)
     assert lib.ysb_num_candidates(ctypes.byref(p), ctypes.byref(n), None) == _lib.YSB_ERR_LIMIT
-    p = _v5_params(mutil_label=True)
+    import oracle
+    from yoloseries_b200 import engine
+    p = engine.make_params("retinanet", oracle.default_hyp(mutil_label=True), 1, 64, 64)  # broken in the reference too
     assert lib.ysb_num_candidates(ctypes.byref(p), ctypes.byref(n), None) == _lib.YSB_ERR_UNSUPPORTED
+    p = _v5_params(mutil_label=True)
+    ws1, ws80 = ctypes.c_size_t(), ctypes.c_size_t()
+    assert lib.ysb_postprocess_workspace_bytes(ctypes.byref(_v5_params()), ctypes.byref(ws1)) == 0
+    assert lib.ysb_postprocess_workspace_bytes(ctypes.byref(p), ctypes.byref(ws80)) == 0
+    assert ws80.value > 70 * ws1.value  # one key slot per (candidate, class)
     p = _v5_params()
     assert lib.ysb_postprocess(ctypes.byref(p), None, 3, None, 0, None, None, None, None) == _lib.YSB_ERR_BAD_ARG
     ws = ctypes.c_size_t()

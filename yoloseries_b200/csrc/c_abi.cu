@@ -33,6 +33,9 @@ static int cuda_status(cudaError_t e)
     return YSB_ERR_CUDA;
 }
 
+// key slots per image: one per candidate, or one per (candidate, class) with mutil_label
+static int64_t key_slots(const Plan &P) { return static_cast<int64_t>(P.N) * (P.multi_label ? P.C : 1); }
+
 struct Built {
     Plan plan;
     int vec;  // 128-bit loads possible for the planes kernel
@@ -60,7 +63,8 @@ static int build_plan(const ysb_params *p, const void *const *d_heads, int num_h
     if (p->anchors_per_cell <= 0 || p->anchors_per_cell > YSB_MAX_ANCHORS) return YSB_ERR_BAD_ARG;
     if (p->num_classes > YSB_MAX_CLASSES) return YSB_ERR_LIMIT;
     if (p->max_det <= 0 || p->max_det > YSB_MAX_DET_LIMIT) return YSB_ERR_LIMIT;
-    if (p->multi_label) return YSB_ERR_UNSUPPORTED;
+    // the reference's multi-label branch is broken for RetinaNet (nonzero(as_tuple=True) on an ndarray)
+    if (p->multi_label && (p->family == YSB_RETINANET || p->family == YSB_RETINANET_EXP)) return YSB_ERR_UNSUPPORTED;
     const int C = p->num_classes;
     const int A = p->anchors_per_cell;
     const int L = p->num_levels;
@@ -88,6 +92,8 @@ static int build_plan(const ysb_params *p, const void *const *d_heads, int num_h
     P.min_box_wh = p->min_box_wh;
     P.pre_nms_topk = p->pre_nms_topk;
     P.obj_col = -1;
+    P.multi_label = p->multi_label != 0;
+    P.multi_strict = p->family == YSB_FCOS;  // eval_fcos.py:247 uses '>', the other families '>='
 
     int64_t n = 0;
     for (int l = 0; l < L; ++l) {
@@ -272,7 +278,7 @@ int ysb_filter_candidates(const ysb_params *p, const void *const *d_heads, int n
     Built b;
     const int st = build_plan(p, d_heads, num_heads, &b);
     if (st != YSB_OK) return st;
-    if (key_capacity < b.plan.N) return YSB_ERR_WORKSPACE;
+    if (key_capacity < key_slots(b.plan)) return YSB_ERR_WORKSPACE;
     return cuda_status(launch_filter(b.plan, b.vec, d_keys, key_capacity, d_counts, static_cast<cudaStream_t>(stream)));
 }
 
@@ -296,7 +302,7 @@ int ysb_postprocess_workspace_bytes(const ysb_params *p, size_t *bytes_out)
     Built b;
     const int st = build_plan(p, nullptr, 0, &b);
     if (st != YSB_OK) return st;
-    *bytes_out = align256(sizeof(uint64_t) * static_cast<size_t>(b.plan.N) * b.plan.batch) +
+    *bytes_out = align256(sizeof(uint64_t) * static_cast<size_t>(key_slots(b.plan)) * b.plan.batch) +
                  align256(sizeof(int32_t) * 4 * static_cast<size_t>(b.plan.batch)) + 256;
     return YSB_OK;
 }
@@ -314,11 +320,12 @@ int ysb_postprocess(const ysb_params *p, const void *const *d_heads, int num_hea
     if (workspace_bytes < need) return YSB_ERR_WORKSPACE;
     uintptr_t base = (reinterpret_cast<uintptr_t>(d_workspace) + 255) & ~static_cast<uintptr_t>(255);
     uint64_t *d_keys = reinterpret_cast<uint64_t *>(base);
-    int32_t *d_counts = reinterpret_cast<int32_t *>(base + align256(sizeof(uint64_t) * static_cast<size_t>(b.plan.N) * b.plan.batch));
+    const int64_t slots = key_slots(b.plan);
+    int32_t *d_counts = reinterpret_cast<int32_t *>(base + align256(sizeof(uint64_t) * static_cast<size_t>(slots) * b.plan.batch));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    st = cuda_status(launch_filter(b.plan, b.vec, d_keys, b.plan.N, d_counts, s));
+    st = cuda_status(launch_filter(b.plan, b.vec, d_keys, slots, d_counts, s));
     if (st != YSB_OK) return st;
-    return cuda_status(launch_select_nms(b.plan, d_keys, b.plan.N, d_counts, d_dets, d_det_idx, d_det_cnt, s));
+    return cuda_status(launch_select_nms(b.plan, d_keys, slots, d_counts, d_dets, d_det_idx, d_det_cnt, s));
 }
 
 int ysb_nms_workspace_bytes(int64_t m, size_t *bytes_out)

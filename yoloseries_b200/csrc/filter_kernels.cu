@@ -812,6 +812,112 @@ __global__ void __launch_bounds__(kRowsTile) k_filter_rows(const __grid_constant
 }
 
 // -------------------------------------------------------------------------------------------------------
+// mutil_label: true -- one record per (candidate, class) whose score reaches the class threshold
+// (trainer/eval_yolov5.py:276-279, eval_yolov7.py:230-233, eval_yolox.py:217-220, eval_yolov8.py:184-187,
+// eval_fcos.py:246-250).  False in every shipped yaml, so this kernel favours simplicity: one thread per candidate,
+// every class evaluated literally (sigmoid, multiply) twice -- once to count, once to write -- any input layout.
+// -------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_filter_multilabel(const __grid_constant__ Plan P, uint64_t *__restrict__ keys,
+                                                           int64_t key_cap, int32_t *__restrict__ counts)
+{
+    const int img = blockIdx.x;
+    const int cand = blockIdx.y * blockDim.x + threadIdx.x;
+    const bool active = cand < P.N;
+    const bool decoded = P.input_kind == YSB_INPUT_DECODED_ROWS;
+    const float *cls = nullptr;
+    size_t cstride = 1;
+    float mult = 1.0f;
+    if (active) {
+        const int l = find_level(P, cand);
+        const LevelDesc &lv = P.lv[l];
+        const int r = cand - lv.cand_off;
+        float objv = 0.0f;
+        if (P.layout == LAYOUT_PLANES) {
+            const int a = r / lv.hw, pos = r - a * lv.hw;
+            cls = lv.p0 + (static_cast<size_t>(img * P.A + a) * P.cls_nch + P.cls_ch) * lv.hw + pos;
+            cstride = static_cast<size_t>(lv.hw);
+            if (P.use_obj)
+                objv = __ldg((P.obj_src == 2 ? lv.p2 : lv.p0) + (static_cast<size_t>(img * P.A + a) * P.obj_nch + P.obj_ch) * lv.hw + pos);
+        } else {
+            const float *row = lv.p0 + (static_cast<size_t>(img) * lv.img_rows + r) * P.row_w_in;
+            cls = row + P.cls_col_in;
+            if (P.use_obj)
+                objv = P.obj_src == 1 ? __ldg(P.lv[0].p1 + (static_cast<size_t>(img) * P.N + cand) * P.reg_row_w + 4)
+                                      : __ldg(row + P.obj_col_in);
+        }
+        if (P.use_obj) mult = decoded ? objv : sigmoid_ref(objv);
+    }
+    auto score_of = [&](int k, float &sk) {
+        const float c = __ldg(cls + static_cast<size_t>(k) * cstride);
+        sk = decoded ? c : sigmoid_ref(c);
+        return P.use_obj ? __fmul_rn(sk, mult) : sk;
+    };
+    auto passes = [&](float p) { return P.multi_strict ? (p > P.cls_thr) : (p >= P.cls_thr); };
+    int n = 0, npre = 0;
+    uint32_t smax_bits = 0u, smin_inv = 0u;
+    if (active) {
+        float smax = -INFINITY, pmax = -INFINITY;
+        for (int k = 0; k < P.C; ++k) {
+            float sk;
+            const float p = score_of(k, sk);
+            smax = fmaxf(smax, sk);
+            pmax = fmaxf(pmax, p);
+            if (sk > P.pre_thr) ++npre;
+            if (passes(p)) {
+                ++n;
+                const uint32_t sb = __float_as_uint(p);
+                smax_bits = max(smax_bits, sb);
+                smin_inv = max(smin_inv, ~sb);
+            }
+        }
+        bool pre = true;
+        switch (P.pre_kind) {
+        case PRE_OBJ: pre = mult >= P.conf_thr; break;
+        case PRE_OBJ_X_MAX: pre = pmax >= P.conf_thr; break;
+        case PRE_MAXCLS: pre = smax >= P.cls_thr; break;
+        case PRE_ANY_GT: pre = smax > P.pre_thr; break;
+        default: break;
+        }
+        if (!pre) { n = 0; smax_bits = 0u; smin_inv = 0u; }
+        if (P.pre_kind != PRE_ANY_GT) npre = 0;
+    }
+    // warp-aggregated reservation of n slots per thread
+    const unsigned lane = threadIdx.x & 31u;
+    int incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= static_cast<unsigned>(d)) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int32_t *cnt = counts + img * 4;
+    const int tp = __reduce_add_sync(0xffffffffu, npre);
+    if (lane == 0 && tp) atomicAdd(cnt + 1, tp);  // FCOS: pairs above pre_nms_thresh (eval_fcos.py:246)
+    if (total == 0) return;
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, smax_bits);
+    const uint32_t wmin = __reduce_max_sync(0xffffffffu, smin_inv);
+    int base = 0;
+    if (lane == 0) {
+        base = atomicAdd(cnt, total);
+        atomicMax(reinterpret_cast<unsigned int *>(cnt + 2), wmax);
+        atomicMax(reinterpret_cast<unsigned int *>(cnt + 3), wmin);
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (n > 0) {
+        int64_t at = static_cast<int64_t>(base) + (incl - n);
+        uint64_t *dst = keys + static_cast<int64_t>(img) * key_cap;
+        for (int k = 0; k < P.C; ++k) {
+            float sk;
+            const float p = score_of(k, sk);
+            if (passes(p)) {
+                if (at < key_cap) dst[at] = pack_key(p, static_cast<uint32_t>(cand), static_cast<uint32_t>(k));
+                ++at;
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------
 // host launchers
 // -------------------------------------------------------------------------------------------------------
 // 1 = direct 128-bit loads (default: fastest measured, profiles/README.md), 0 = cp.async private rings,
@@ -831,6 +937,11 @@ cudaError_t launch_filter(const Plan &P, int vec, uint64_t *d_keys, int64_t key_
     cudaError_t e = cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * 4 * static_cast<size_t>(P.batch), stream);
     if (e != cudaSuccess) return e;
     if (P.batch == 0 || P.N == 0) return cudaSuccess;
+    if (P.multi_label) {
+        const dim3 grid(P.batch, (P.N + 255) / 256);
+        k_filter_multilabel<<<grid, 256, 0, stream>>>(P, d_keys, key_cap, d_counts);
+        return cudaGetLastError();
+    }
     if (P.layout == LAYOUT_PLANES && vec == 4 && g_filter_variant != 1) {  // ring variants need every level vectorised
         static int num_sms = 0;
         if (num_sms == 0) {

@@ -226,11 +226,12 @@ class PostProcessor:
         kind = _lib.INPUT_DECODED_ROWS if decoded else _lib.INPUT_RAW_HEADS
         ent = self._prepare(flat, batch, img_h, img_w, kind)
         dev = flat[0].device
-        keys = torch.empty((batch, ent["N"]), dtype=torch.int64, device=dev)
+        slots = ent["N"] * (int(self.hyp["num_class"]) if self.hyp["mutil_label"] else 1)
+        keys = torch.empty((batch, slots), dtype=torch.int64, device=dev)
         counts = torch.empty((batch, 4), dtype=torch.int32, device=dev)
         ptrs = _lib.head_pointer_array(flat)
         _lib.check(self._lib.ysb_filter_candidates(ctypes.byref(ent["params"]), ptrs, len(flat), keys.data_ptr(),
-                                                   ent["N"], counts.data_ptr(), self._stream()),
+                                                   slots, counts.data_ptr(), self._stream()),
                    "ysb_filter_candidates")
         return keys, counts
 
