@@ -15,86 +15,151 @@ namespace ysb {
 constexpr int kDecRows = 32;
 constexpr int kDecThreads = 256;
 
-// class / objectness column value of the decoded row for raw heads
-__device__ __forceinline__ float decoded_class_value(const Plan &P, int img, int cand, int l, int k)
+// Address of class logit 0 of a candidate and the stride between consecutive classes (hoisted out of the class loop:
+// the level lookup and the two integer divisions are per candidate, not per element).
+struct CandAddr {
+    const float *cls;
+    size_t cstride;
+    const float *obj;  // objectness / centerness / conf logit, nullptr when the family has none
+};
+
+__device__ __forceinline__ CandAddr cand_addr(const Plan &P, int img, int cand)
 {
+    CandAddr c;
+    const int l = find_level(P, cand);
     const LevelDesc &lv = P.lv[l];
     const int r = cand - lv.cand_off;
+    c.obj = nullptr;
     if (P.layout == LAYOUT_PLANES) {
         const int a = r / lv.hw, pos = r - a * lv.hw;
-        return sigmoid_ref(__ldg(lv.p0 + (static_cast<size_t>(img * P.A + a) * P.cls_nch + P.cls_ch + k) * lv.hw + pos));
+        c.cls = lv.p0 + (static_cast<size_t>(img * P.A + a) * P.cls_nch + P.cls_ch) * lv.hw + pos;
+        c.cstride = static_cast<size_t>(lv.hw);
+        if (P.obj_col >= 0)
+            c.obj = (P.obj_src == 2 ? lv.p2 : lv.p0) + (static_cast<size_t>(img * P.A + a) * P.obj_nch + P.obj_ch) * lv.hw + pos;
+    } else {
+        const float *row = lv.p0 + (static_cast<size_t>(img) * lv.img_rows + r) * P.row_w_in;
+        c.cls = row + P.cls_col_in;
+        c.cstride = 1;
+        if (P.obj_col >= 0)
+            c.obj = P.obj_src == 1 ? P.lv[0].p1 + (static_cast<size_t>(img) * P.N + cand) * P.reg_row_w + 4 : row + P.obj_col_in;
     }
-    return sigmoid_ref(__ldg(lv.p0 + (static_cast<size_t>(img) * lv.img_rows + r) * P.row_w_in + P.cls_col_in + k));
+    return c;
 }
 
-__device__ __forceinline__ float decoded_obj_value(const Plan &P, int img, int cand, int l)
-{
-    const LevelDesc &lv = P.lv[l];
-    const int r = cand - lv.cand_off;
-    if (P.obj_src == 1)
-        return sigmoid_ref(__ldg(P.lv[0].p1 + (static_cast<size_t>(img) * P.N + cand) * P.reg_row_w + 4));
-    if (P.layout == LAYOUT_PLANES) {
-        const int a = r / lv.hw, pos = r - a * lv.hw;
-        const float *src = (P.obj_src == 2 ? lv.p2 : lv.p0);
-        return sigmoid_ref(__ldg(src + (static_cast<size_t>(img * P.A + a) * P.obj_nch + P.obj_ch) * lv.hw + pos));
-    }
-    return sigmoid_ref(__ldg(lv.p0 + (static_cast<size_t>(img) * lv.img_rows + r) * P.row_w_in + P.obj_col_in));
-}
-
+// ROWS = candidates per CTA: 32 for channels-last heads (their rows are contiguous anyway), 128 for NCHW planes so that
+// every plane access of a CTA covers 512 contiguous bytes.
+template <int ROWS>
 __global__ void __launch_bounds__(kDecThreads) k_decode_rows(const __grid_constant__ Plan P, float *__restrict__ out)
 {
-    extern __shared__ float tile[];  // [kDecRows][row_w]
+    extern __shared__ __align__(16) float tile[];  // [ROWS][row_w]
     const int img = blockIdx.y;
-    const int c0 = blockIdx.x * kDecRows;
-    const int nrows = min(kDecRows, P.N - c0);
+    const int c0 = blockIdx.x * ROWS;
+    const int nrows = min(ROWS, P.N - c0);
     const int rw = P.row_w;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int kWarps = kDecThreads / 32;
     if (P.layout == LAYOUT_PLANES) {
-        // lane = candidate, warps stride over the class columns: each load instruction covers 32 neighbouring
-        // positions of one plane (candidates of a CTA may straddle an anchor/level boundary; still correct)
-        const int cand = c0 + lane;
-        if (lane < nrows) {
-            const int l = find_level(P, cand);
-            for (int k = warp; k < P.C; k += kWarps) tile[lane * rw + P.cls_col + k] = decoded_class_value(P, img, cand, l, k);
-            if (warp == 0) {
-                const float4 b = decode_box_cols(P, img, cand);
-                float *t = tile + lane * rw + P.box_col;
-                t[0] = b.x; t[1] = b.y; t[2] = b.z; t[3] = b.w;
+        // thread = (candidate, class phase): consecutive threads take consecutive positions of one plane; four
+        // independent loads in flight per thread, then four sigmoids
+        constexpr int kPhases = kDecThreads / ROWS;  // 2 for ROWS = 128
+        const int rr = threadIdx.x % ROWS, ph = threadIdx.x / ROWS;
+        if (rr < nrows) {
+            const CandAddr ca = cand_addr(P, img, c0 + rr);
+            float *tc = tile + rr * rw + P.cls_col;
+            const size_t step = static_cast<size_t>(kPhases) * ca.cstride;
+            int k = ph;
+            const float *src = ca.cls + static_cast<size_t>(k) * ca.cstride;
+            for (; k + 3 * kPhases < P.C; k += 4 * kPhases, src += 4 * step) {
+                const float v0 = __ldg(src), v1 = __ldg(src + step), v2 = __ldg(src + 2 * step), v3 = __ldg(src + 3 * step);
+                tc[k] = sigmoid_ref(v0);
+                tc[k + kPhases] = sigmoid_ref(v1);
+                tc[k + 2 * kPhases] = sigmoid_ref(v2);
+                tc[k + 3 * kPhases] = sigmoid_ref(v3);
             }
-            if (warp == 1 % kWarps && P.obj_col >= 0) tile[lane * rw + P.obj_col] = decoded_obj_value(P, img, cand, l);
+            for (; k < P.C; k += kPhases, src += step) tc[k] = sigmoid_ref(__ldg(src));
+            if (ph == 0 && ca.obj) tile[rr * rw + P.obj_col] = sigmoid_ref(__ldg(ca.obj));
+        }
+        if (P.family == YSB_YOLOV8) {
+            // DFL boxes: four threads per candidate (one side each), 64 candidates per round
+            for (int base = 0; base < nrows; base += kDecThreads / 4) {
+                const int r4 = base + (threadIdx.x >> 2), side = threadIdx.x & 3;
+                float sv = 0.0f;
+                if (r4 < nrows) sv = v8_side_value(P, img, c0 + r4, side);
+                const unsigned qb = lane & ~3u;
+                const float s0 = __shfl_sync(0xffffffffu, sv, qb), s1 = __shfl_sync(0xffffffffu, sv, qb + 1);
+                const float s2 = __shfl_sync(0xffffffffu, sv, qb + 2), s3 = __shfl_sync(0xffffffffu, sv, qb + 3);
+                if (side == 0 && r4 < nrows) {
+                    const float4 b = v8_box_from_sides(P, c0 + r4, s0, s1, s2, s3);
+                    float *t = tile + r4 * rw + P.box_col;
+                    t[0] = b.x; t[1] = b.y; t[2] = b.z; t[3] = b.w;
+                }
+            }
+        } else if (threadIdx.x >= kDecThreads - ROWS && threadIdx.x - (kDecThreads - ROWS) < nrows) {
+            const int rb = threadIdx.x - (kDecThreads - ROWS);
+            const float4 b = decode_box_cols(P, img, c0 + rb);
+            float *t = tile + rb * rw + P.box_col;
+            t[0] = b.x; t[1] = b.y; t[2] = b.z; t[3] = b.w;
         }
     } else {
-        // warp = candidate row, lanes stride over its columns (contiguous in the channels-last head)
-        for (int r = warp; r < nrows; r += kWarps) {
-            const int cand = c0 + r;
-            const int l = find_level(P, cand);
-            for (int k = lane; k < P.C; k += 32) tile[r * rw + P.cls_col + k] = decoded_class_value(P, img, cand, l, k);
-            if (lane == 0) {
-                const float4 b = decode_box_cols(P, img, cand);
-                float *t = tile + r * rw + P.box_col;
-                t[0] = b.x; t[1] = b.y; t[2] = b.z; t[3] = b.w;
+        // eight threads per candidate row (32 rows x 8): a warp reads 4 rows x 32 contiguous bytes per step, every
+        // fetched sector fully used; four loads in flight per thread.  Lane-per-candidate box / objectness decode.
+        const int r = threadIdx.x >> 3, q = threadIdx.x & 7;
+        if (r < nrows) {
+            const CandAddr ca = cand_addr(P, img, c0 + r);
+            float *tc = tile + r * rw + P.cls_col;
+            int k = q;
+            for (; k + 24 < P.C; k += 32) {
+                const float v0 = __ldg(ca.cls + k), v1 = __ldg(ca.cls + k + 8), v2 = __ldg(ca.cls + k + 16), v3 = __ldg(ca.cls + k + 24);
+                tc[k] = sigmoid_ref(v0);
+                tc[k + 8] = sigmoid_ref(v1);
+                tc[k + 16] = sigmoid_ref(v2);
+                tc[k + 24] = sigmoid_ref(v3);
             }
-            if (lane == 1 && P.obj_col >= 0) tile[r * rw + P.obj_col] = decoded_obj_value(P, img, cand, l);
+            for (; k < P.C; k += 8) tc[k] = sigmoid_ref(__ldg(ca.cls + k));
+        }
+        if (warp == 0 && lane < nrows) {
+            const int cand = c0 + lane;
+            const float4 b = decode_box_cols(P, img, cand);
+            float *t = tile + lane * rw + P.box_col;
+            t[0] = b.x; t[1] = b.y; t[2] = b.z; t[3] = b.w;
+            if (P.obj_col >= 0) {
+                const CandAddr ca = cand_addr(P, img, cand);
+                t[P.obj_col - P.box_col] = sigmoid_ref(__ldg(ca.obj));
+            }
         }
     }
     __syncthreads();
     float *dst = out + (static_cast<size_t>(img) * P.N + c0) * rw;
     const int nfl = nrows * rw;
-    for (int e = threadIdx.x; e < nfl; e += kDecThreads) dst[e] = tile[e];
+    if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(tile)) & 15u) == 0) {
+        const int nv = nfl >> 2;
+        for (int e = threadIdx.x; e < nv; e += kDecThreads)
+            reinterpret_cast<float4 *>(dst)[e] = reinterpret_cast<const float4 *>(tile)[e];
+        for (int e = (nv << 2) + threadIdx.x; e < nfl; e += kDecThreads) dst[e] = tile[e];
+    } else {
+        for (int e = threadIdx.x; e < nfl; e += kDecThreads) dst[e] = tile[e];
+    }
+}
+
+template <int ROWS>
+static cudaError_t launch_decode_t(const Plan &P, float *d_out, cudaStream_t stream)
+{
+    const size_t smem = static_cast<size_t>(ROWS) * P.row_w * sizeof(float);
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_decode_rows<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+    }
+    const dim3 grid((P.N + ROWS - 1) / ROWS, P.batch);
+    k_decode_rows<ROWS><<<grid, kDecThreads, smem, stream>>>(P, d_out);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_decode(const Plan &P, float *d_out, cudaStream_t stream)
 {
     if (P.batch == 0 || P.N == 0) return cudaSuccess;
-    const size_t smem = static_cast<size_t>(kDecRows) * P.row_w * sizeof(float);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_decode_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) return e;
-    }
-    const dim3 grid((P.N + kDecRows - 1) / kDecRows, P.batch);
-    k_decode_rows<<<grid, kDecThreads, smem, stream>>>(P, d_out);
-    return cudaGetLastError();
+    if (P.layout == LAYOUT_PLANES && static_cast<size_t>(128) * P.row_w * sizeof(float) <= 100 * 1024)
+        return launch_decode_t<128>(P, d_out, stream);
+    return launch_decode_t<32>(P, d_out, stream);
 }
 
 }  // namespace ysb
