@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--family", default="yolov5")
     ap.add_argument("--img", type=int, default=640)
     ap.add_argument("--dist", default="dense", choices=["dense", "sparse", "crowd"])
-    ap.add_argument("--pipeline", type=int, default=2, help="0: serial; 1: NMS kernel of batch i overlaps the filter kernel of batch i+1 on a side stream; 2: same, side stream at high priority")
+    ap.add_argument("--pipeline", type=int, default=3, help="0: serial; 1: NMS kernel of batch i overlaps the filter kernel of batch i+1 on a side stream; 2: same, side stream at high priority; 3: two independent lanes (step i entirely on stream i %% 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-images", type=int, default=2, help="images in the bounded CPU-baseline sample")
     return ap.parse_args()
@@ -250,7 +250,7 @@ def run_ours(args):
 
     # Two slots + two streams: the select/sort/NMS kernel of batch i (64 CTAs, latency-bound) runs on the side stream
     # while the HBM-bound filter kernel of batch i+1 streams on the main one.  --pipeline 0 serialises them.
-    slots = [Slot(), Slot()] if args.pipeline else [Slot()]
+    slots = [Slot(), Slot()] if args.pipeline else [Slot()]  # mode 3: slot i % 2 lives on lane i % 2
     stream = torch.cuda.current_stream()
     side = torch.cuda.Stream(device=dev, priority=-1 if args.pipeline == 2 else 0) if args.pipeline else stream
 
@@ -265,10 +265,29 @@ def run_ours(args):
                                       sl.cnt.data_ptr(), ctypes.c_void_p(st.cuda_stream)), "ysb_select_nms")
 
     step_no = [0]
+    lanes = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)] if args.pipeline == 3 else None
 
     def step(ev=None, head_ptrs=None):
         head_ptrs = head_ptrs or ptrs
         sl = slots[step_no[0] % len(slots)]
+        if args.pipeline == 3:
+            # two independent lanes: step i runs filter -> NMS (-> all-gather) in order on stream i % 2, so the NMS
+            # kernel of one step overlaps the filter kernel of the next without any cross-stream event
+            st = lanes[step_no[0] % 2]
+            step_no[0] += 1
+            if ev:
+                ev[0].record(st)
+            launch_filter(head_ptrs, sl, st)
+            if ev:
+                ev[1].record(st)
+                ev[2].record(st)
+            launch_nms(head_ptrs, sl, st)
+            if ev:
+                ev[3].record(st)
+            if world > 1:
+                with torch.cuda.stream(st):
+                    dist.all_gather_into_tensor(sl.gathered.view(-1), sl.flat_send)
+            return sl
         step_no[0] += 1
         if args.pipeline:
             stream.wait_event(sl.done)       # the slot's previous batch has left the NMS stage
@@ -292,8 +311,16 @@ def run_ours(args):
             sl.done.record(side)
         return sl
 
+    def fork():
+        if args.pipeline == 3:  # the lanes start after whatever the main stream has queued (e_beg, H2D copies)
+            lanes[0].wait_stream(stream)
+            lanes[1].wait_stream(stream)
+
     def drain():
-        if args.pipeline:
+        if args.pipeline == 3:
+            stream.wait_stream(lanes[0])
+            stream.wait_stream(lanes[1])
+        elif args.pipeline:
             stream.wait_stream(side)
 
     sampler = ClockSampler(local) if rank == 0 else None
@@ -315,6 +342,7 @@ def run_ours(args):
     if sampler:
         sampler.arm(True)  # sampled through the timed region and the identical-load hold phase that follows it
     e_beg.record(stream)
+    fork()
     for k in range(args.steps):
         step(evs[k])
     drain()
@@ -362,6 +390,7 @@ def run_ours(args):
     def e2e_step():
         for d, h in zip(dev_heads, host_heads):
             d.copy_(h, non_blocking=True)
+        fork()
         sl = step(None, ptrs2)
         drain()
         host_dets.copy_(sl.dets, non_blocking=True)

@@ -492,11 +492,9 @@ static cudaError_t launch_bulk(const Plan &P, int num_sms, uint64_t *d_keys, int
     cfg.items_per_img = items;
     const int total = items * P.batch;
     const size_t smem = stage_bytes * stages + 2 * sizeof(uint64_t) * stages;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
+    {
         cudaError_t e = cudaFuncSetAttribute(k_filter_planes_bulk<CW, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
-        smem_set = smem;
     }
     const int grid = total < num_sms ? total : num_sms;
     k_filter_planes_bulk<CW, PL><<<grid, kBulkThreads, smem, stream>>>(P, cfg, total, d_keys, key_cap, d_counts);
@@ -706,11 +704,9 @@ static cudaError_t launch_async(const Plan &P, int num_sms, uint64_t *d_keys, in
 {
     const int64_t total_units = static_cast<int64_t>(P.units_per_img) * P.batch;
     const size_t smem = static_cast<size_t>(NG) * G * 16 * THREADS;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
+    {
         cudaError_t e = cudaFuncSetAttribute(k_filter_planes_async<THREADS, G, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
-        smem_set = smem;
     }
     int ctas_per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
     if (ctas_per_sm * THREADS > 2048) ctas_per_sm = 2048 / THREADS;
@@ -943,14 +939,11 @@ cudaError_t launch_filter(const Plan &P, int vec, uint64_t *d_keys, int64_t key_
         return cudaGetLastError();
     }
     if (P.layout == LAYOUT_PLANES && vec == 4 && g_filter_variant != 1) {  // ring variants need every level vectorised
-        static int num_sms = 0;
-        if (num_sms == 0) {
-            int dev = 0;
-            e = cudaGetDevice(&dev);
-            if (e != cudaSuccess) return e;
-            e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-            if (e != cudaSuccess) return e;
-        }
+        int num_sms = 0, dev = 0;
+        e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
         const int nq = P.C + (P.use_obj ? 1 : 0);
         const bool nine = nq % 9 == 0 || P.C % 9 == 0;  // e.g. 80 classes + objectness = 9 x 9 planes
         if (g_filter_variant == 2) {  // TMA bulk-copy ring (profiling variant)

@@ -560,13 +560,11 @@ cudaError_t launch_select_nms(const Plan &P, const uint64_t *d_keys, int64_t key
                               float *d_dets, int32_t *d_det_idx, int32_t *d_det_cnt, cudaStream_t stream)
 {
     if (P.batch == 0) return cudaSuccess;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_select_nms<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(sizeof(NmsSmem)));
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    // per-device attribute; set on every launch (host-side, sub-microsecond) so that a process driving several
+    // devices never launches with the default 48 KB limit
+    cudaError_t e = cudaFuncSetAttribute(k_select_nms<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(sizeof(NmsSmem)));
+    if (e != cudaSuccess) return e;
     ArrayArgs aa{};
     k_select_nms<false><<<P.batch, kThreads, sizeof(NmsSmem), stream>>>(P, d_keys, key_cap, d_counts, d_dets, d_det_idx,
                                                                          d_det_cnt, aa);
@@ -617,12 +615,8 @@ cudaError_t launch_array_nms(const float *d_boxes, const float *d_scores, int64_
     cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int32_t) * 4, stream);
     if (e != cudaSuccess) return e;
     k_array_keys<<<static_cast<unsigned>((m + 255) / 256), 256, 0, stream>>>(d_scores, static_cast<int>(m), keys, counts);
-    static bool attr_set = false;
-    if (!attr_set) {
-        e = cudaFuncSetAttribute(k_select_nms<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(NmsSmem)));
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    e = cudaFuncSetAttribute(k_select_nms<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(NmsSmem)));
+    if (e != cudaSuccess) return e;
     Plan P;
     memset(&P, 0, sizeof(P));
     P.batch = 1;
