@@ -175,3 +175,22 @@ def test_multi_label_mode(family, img, dist):
         hyp.update(iou_threshold=0.35, max_predictions_per_img=100)
     heads = synth.make_heads(family, 2, img, img, 20, dist, seed=31, device="cuda")
     _check_against_oracle(family, heads, img, img, hyp)
+
+
+def test_pipelined_processor_matches_serial():
+    from yoloseries_b200 import synth
+    from yoloseries_b200.engine import PipelinedPostProcessor
+    hyp = oracle.default_hyp()
+    anchors = torch.tensor(synth.V5_ANCHORS_PX)
+    ppp = PipelinedPostProcessor("yolov5", hyp, anchors=anchors, lanes=3)
+    serial = _pp("yolov5", hyp)
+    batches = [synth.make_heads("yolov5", 3, 320, 320, 80, d, seed=40 + i, device="cuda")
+               for i, d in enumerate(["dense", "crowd", "sparse"])]
+    tickets = [ppp.submit(h, 320, 320) for h in batches]
+    for h, t in zip(batches, tickets):
+        got = ppp.result(t, as_numpy=True)
+        want = serial.to_list(serial.run(h, 320, 320), as_numpy=True)
+        for g, w in zip(got, want):
+            assert (g is None) == (w is None)
+            if g is not None:
+                np.testing.assert_array_equal(g, w)

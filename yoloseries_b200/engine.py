@@ -253,3 +253,43 @@ class PostProcessor:
             if with_index:
                 ids.append(idx[i, :c].clone().numpy())
         return (res, ids) if with_index else res
+
+
+class PipelinedPostProcessor:
+    """Several batches in flight: batch i runs filter -> NMS on CUDA stream ``i % lanes`` with its own buffers, so the
+    latency-bound NMS kernel of one batch overlaps the HBM-bound filter kernel of the next ones (bench.py's default
+    mode; 4 lanes hide the NMS kernel completely at 64 images per batch).
+
+        t = ppp.submit(heads, h, w)      # returns immediately
+        dets = ppp.result(t)             # list[Tensor(K,6) | None], blocks on that batch only
+
+    A ticket's buffers are reused ``lanes`` submissions later: fetch results before submitting that many new batches.
+    """
+
+    def __init__(self, family, hyp, anchors=None, compute_metric=False, lanes=4):
+        self._pps = [PostProcessor(family, hyp, anchors, compute_metric) for _ in range(lanes)]
+        self._streams = None
+        self._next = 0
+
+    def submit(self, heads, img_h, img_w, decoded=False):
+        flat = [heads] if decoded else flatten_heads(self._pps[0].family, heads)
+        dev = flat[0].device
+        if self._streams is None:
+            self._streams = [torch.cuda.Stream(device=dev) for _ in self._pps]
+        i = self._next
+        self._next = (i + 1) % len(self._pps)
+        st = self._streams[i]
+        st.wait_stream(torch.cuda.current_stream(dev))  # the heads were produced on the caller's stream
+        with torch.cuda.stream(st):
+            out = self._pps[i].run(heads, img_h, img_w, decoded=decoded)
+            done = torch.cuda.Event()
+            done.record(st)
+        for t in flat:
+            t.record_stream(st)
+        return (i, done, out)
+
+    def result(self, ticket, as_numpy=False, with_index=False):
+        i, done, out = ticket
+        done.synchronize()
+        with torch.cuda.stream(self._streams[i]):
+            return PostProcessor.to_list(out, as_numpy=as_numpy, with_index=with_index)
