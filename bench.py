@@ -238,21 +238,37 @@ def run_ours(args):
         """Intermediates + outputs of one in-flight batch.  `flat_send` = [rows (b, max_det, 6) f32 | counts (b) i32]:
         the NMS kernel writes straight into it and, at N > 1, it is the fixed-stride send buffer of the all-gather."""
 
-        def __init__(self):
+        def __init__(self, send_row=None):
             self.keys = torch.empty((args.batch, N), dtype=torch.int64, device=dev)
             self.counts = torch.zeros((args.batch, 4), dtype=torch.int32, device=dev)
-            self.flat_send = torch.zeros(n_row_f + args.batch, dtype=torch.float32, device=dev)
+            self.flat_send = send_row if send_row is not None else torch.zeros(n_row_f + args.batch, dtype=torch.float32, device=dev)
             self.dets = self.flat_send[:n_row_f].view(args.batch, max_det, 6)
             self.cnt = self.flat_send[n_row_f:].view(torch.int32)
             self.idx = torch.empty((args.batch, max_det), dtype=torch.int32, device=dev)
             self.gathered = torch.empty((world, n_row_f + args.batch), dtype=torch.float32, device=dev) if world > 1 else None
             self.filtered = torch.cuda.Event()
             self.done = torch.cuda.Event()
+            self.nms_done = torch.cuda.Event()
 
     # Two slots + two streams: the select/sort/NMS kernel of batch i (64 CTAs, latency-bound) runs on the side stream
     # while the HBM-bound filter kernel of batch i+1 streams on the main one.  --pipeline 0 serialises them.
     n_lanes = max(2, args.lanes) if args.pipeline == 3 else 2
-    slots = [Slot() for _ in range(n_lanes)] if args.pipeline else [Slot()]  # mode 3: slot i % L lives on lane i % L
+    # mode 3: slot i % L lives on lane i % L.  At N > 1 the L send buffers are rows of ONE tensor, all-gathered once per
+    # L steps (one NCCL launch per cycle instead of per step: the exchange is latency-bound, 461 kB per rank and step).
+    big_send = torch.zeros((n_lanes, n_row_f + args.batch), dtype=torch.float32, device=dev) if args.pipeline == 3 else None
+    big_recv = torch.empty((world, n_lanes, n_row_f + args.batch), dtype=torch.float32, device=dev) if (world > 1 and args.pipeline == 3) else None
+    slots = ([Slot(big_send[i]) for i in range(n_lanes)] if args.pipeline == 3 else [Slot(), Slot()]) if args.pipeline else [Slot()]
+    comm = torch.cuda.Stream(device=dev) if (world > 1 and args.pipeline == 3) else None
+    gathered_ev = torch.cuda.Event()
+
+    def gather_cycle():
+        """all-gather of the L most recent batches' rows+counts on the comm stream"""
+        for sl_ in slots:
+            comm.wait_event(sl_.nms_done)
+        with torch.cuda.stream(comm):
+            dist.all_gather_into_tensor(big_recv.view(-1), big_send.view(-1))
+        gathered_ev.record(comm)
+
     stream = torch.cuda.current_stream()
     side = torch.cuda.Stream(device=dev, priority=-1 if args.pipeline == 2 else 0) if args.pipeline else stream
 
@@ -283,12 +299,15 @@ def run_ours(args):
             if ev:
                 ev[1].record(st)
                 ev[2].record(st)
+            if comm is not None:
+                st.wait_event(gathered_ev)   # the slot's send row may be overwritten only after its cycle was gathered
             launch_nms(head_ptrs, sl, st)
             if ev:
                 ev[3].record(st)
-            if world > 1:
-                with torch.cuda.stream(st):
-                    dist.all_gather_into_tensor(sl.gathered.view(-1), sl.flat_send)
+            if comm is not None:
+                sl.nms_done.record(st)
+                if step_no[0] % n_lanes == 0:
+                    gather_cycle()
             return sl
         step_no[0] += 1
         if args.pipeline:
@@ -320,6 +339,10 @@ def run_ours(args):
 
     def drain():
         if args.pipeline == 3:
+            if comm is not None:
+                if step_no[0] % n_lanes != 0:   # a partial last cycle still has to be exchanged
+                    gather_cycle()
+                stream.wait_stream(comm)
             for ln in lanes:
                 stream.wait_stream(ln)
         elif args.pipeline:
