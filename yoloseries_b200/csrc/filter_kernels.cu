@@ -154,7 +154,7 @@ __device__ __forceinline__ void emit_keys(const uint64_t (&k)[VEC], unsigned okm
 // planes layout (NCHW heads: YOLOv5, YOLOX, YOLOv8, FCOS).  One thread = VEC consecutive positions of one
 // (image, anchor); per class plane a warp reads 32*VEC*4 contiguous bytes (512 B with 128-bit loads).
 // -------------------------------------------------------------------------------------------------------
-template <int VEC, int U = 8, int THREADS = 256, int MINB = 1, int HINT = 0>
+template <int VEC, int U = 8, int THREADS = 256, int MINB = 1, int HINT = 0, int PROBE = 0>
 __global__ void __launch_bounds__(THREADS, MINB) k_filter_planes(const __grid_constant__ Plan P, uint64_t *__restrict__ keys,
                                                                  int64_t key_cap, int32_t *__restrict__ counts)
 {
@@ -209,7 +209,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_filter_planes(const __grid_co
 #pragma unroll
             for (int q = 0; q < U; ++q)
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) top2_update(v[q][j], k + q, m1[j], m2[j], k0[j]);
+                for (int j = 0; j < VEC; ++j) {
+                    if (PROBE) m1[j] = fmaxf(m1[j], v[q][j]);  // profiling aid: same loads, 1 ALU op per logit
+                    else top2_update(v[q][j], k + q, m1[j], m2[j], k0[j]);
+                }
         }
         for (; k < P.C; ++k) {
             float v[VEC];
@@ -982,6 +985,7 @@ cudaError_t launch_filter(const Plan &P, int vec, uint64_t *d_keys, int64_t key_
             case 10: k_filter_planes<4, 10, 128, 6><<<grid128, 128, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
             case 11: k_filter_planes<4, 20, 128, 4><<<grid128, 128, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
             case 1: k_filter_planes<4><<<grid, 256, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
+            case 20: k_filter_planes<4, 16, 128, 4, 1, 1><<<grid128, 128, 0, stream>>>(P, d_keys, key_cap, d_counts); break;  // load-pattern probe
             // default: 128-thread CTAs, 16 loads of 128 bits in flight per thread, 256-byte L2 prefetch granularity
             default: k_filter_planes<4, 16, 128, 4, 1><<<grid128, 128, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
             }
