@@ -159,6 +159,40 @@ def cpu_images_per_second(heads_np, threads):
     return n_images / dt, dt
 
 
+def parity_counters(args, pp, heads, slot, hyp, n_check=2):
+    """North-star parity report on the first images of the bench batch (oracle = checker only, outside the timed
+    region): decoded max relative error vs the numpy restatement, kept rows / candidate indices vs the oracle applied
+    to the GPU-decoded tensor, and how many visited IoUs sit within 1e-6 of the threshold."""
+    import numpy as np
+    import oracle
+    import torch
+
+    sub = [h[:n_check].contiguous() for h in heads]
+    dec_gpu = pp.decode(sub, args.img, args.img).cpu().numpy()
+    dec_ref = oracle.decode_yolov5([h.cpu().numpy() for h in sub])
+    rel = np.abs(dec_gpu - dec_ref) / np.maximum(np.abs(dec_ref), 1.0)
+    want = oracle.evaluator_nms("yolov5", dec_gpu, hyp)
+    torch.cuda.synchronize()
+    rows_ok = idx_ok = True
+    near = 0
+    cnt = slot.cnt[:n_check].cpu().numpy()
+    for i, w in enumerate(want):
+        k = int(cnt[i])
+        got_rows = slot.dets[i, :max(k, 0)].cpu().numpy()
+        got_idx = slot.idx[i, :max(k, 0)].cpu().numpy()
+        if w.rows is None:
+            rows_ok &= k < 0
+            continue
+        rows_ok &= got_rows.shape == w.rows.shape and bool(np.array_equal(got_rows, w.rows))
+        idx_ok &= bool(np.array_equal(got_idx, w.cand_index))
+        order = np.lexsort((np.arange(len(w.nms_scores)), -w.nms_scores.astype(np.float64)))[:4096]
+        iou = oracle.numba_iou(w.nms_boxes[np.asarray(w.keep, dtype=np.int64)], w.nms_boxes[order])
+        near += int(np.sum(np.abs(iou - hyp["iou_threshold"]) < 1e-6))
+    return {"images_checked": n_check, "decoded_max_rel_err": float(rel.max()), "decoded_within_1e-5": bool(rel.max() <= 1e-5),
+            "kept_rows_bit_exact": bool(rows_ok), "kept_indices_bit_exact": bool(idx_ok),
+            "iou_within_1e-6_of_threshold": near}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -493,6 +527,7 @@ def run_ours(args):
                 "value": v, "unit": UNIT, "cores": 1, "kind": "port",
                 "sample": f"{args.cpu_images} images of the same workload on 1 host thread ({dt:.1f} s): C/numpy port "
                           "of the reference algorithm incl. the full greedy NMS loop (no early stop)"}
+            line["parity"] = parity_counters(args, pp, heads, slots[0], hyp)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

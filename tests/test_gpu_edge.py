@@ -194,3 +194,36 @@ def test_pipelined_processor_matches_serial():
             assert (g is None) == (w is None)
             if g is not None:
                 np.testing.assert_array_equal(g, w)
+
+
+@pytest.mark.parametrize("thr", [0.5, 0.25, 1.0 / 3.0, 0.2, 0.75])
+def test_iou_exactly_at_threshold(thr):
+    """Integer-coordinate boxes give exactly representable IoUs (1/2, 1/4, 1/3 rounded, ...): the '>=' of numba_nms
+    versus the '>' of the count filter must both be reproduced on the boundary, with many tied scores."""
+    from yoloseries_b200.utils import numba_nms
+    rng = np.random.default_rng(int(thr * 1000))
+    m = 600
+    xy = rng.integers(0, 24, size=(m, 2)).astype(np.float32)
+    wh = rng.integers(1, 9, size=(m, 2)).astype(np.float32)
+    boxes = np.concatenate((xy, xy + wh), axis=1)
+    scores = (rng.integers(1, 12, size=m) / 12.0).astype(np.float32)   # heavy ties
+    ref = oracle.numba_nms(boxes, scores, thr)
+    iou = oracle.numba_iou(boxes, boxes)
+    assert np.sum(iou == thr) > 0 or thr in (1.0 / 3.0, 0.2)             # the boundary really is exercised
+    assert numba_nms(boxes, scores, thr) == ref
+
+
+def test_count_filter_exactly_at_threshold():
+    """postprocess_bbox uses a strict '>' on the same IoU: a neighbour at exactly the threshold must not count."""
+    hyp = oracle.default_hyp(num_class=1, iou_threshold=0.5, conf_threshold=0.0, cls_threshold=0.0)
+    # decoded rows [cx, cy, w, h, obj, cls0] for yolov5 -> two boxes with IoU exactly 0.5, one isolated box
+    dec = np.zeros((1, 3, 6), dtype=np.float32)
+    dec[0, 0] = [1.0, 0.5, 2.0, 1.0, 0.9, 1.0]     # [0,0,2,1]
+    dec[0, 1] = [0.5, 0.5, 1.0, 1.0, 0.8, 1.0]     # [0,0,1,1]  IoU with the first = 0.5
+    dec[0, 2] = [10.0, 10.0, 2.0, 2.0, 0.7, 1.0]
+    want = oracle.evaluator_nms("yolov5", dec, hyp)
+    pp = _pp("yolov5", hyp)
+    out = pp.run(torch.from_numpy(dec).cuda(), 640, 640, decoded=True)
+    rows = pp.to_list(out, as_numpy=True)
+    assert want[0].rows is not None and rows[0] is not None
+    np.testing.assert_array_equal(rows[0], want[0].rows)
