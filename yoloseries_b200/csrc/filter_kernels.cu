@@ -986,8 +986,12 @@ cudaError_t launch_filter(const Plan &P, int vec, uint64_t *d_keys, int64_t key_
             case 11: k_filter_planes<4, 20, 128, 4><<<grid128, 128, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
             case 1: k_filter_planes<4><<<grid, 256, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
             case 20: k_filter_planes<4, 16, 128, 4, 1, 1><<<grid128, 128, 0, stream>>>(P, d_keys, key_cap, d_counts); break;  // load-pattern probe
-            // default: 128-thread CTAs, 16 loads of 128 bits in flight per thread, 256-byte L2 prefetch granularity
-            default: k_filter_planes<4, 16, 128, 4, 1><<<grid128, 128, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
+            case 21: k_filter_planes<4, 8, 256, 4, 1><<<grid, 256, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
+            case 22: k_filter_planes<4, 8, 128, 8, 1><<<grid128, 128, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
+            case 24: k_filter_planes<4, 16, 128, 4, 1><<<grid128, 128, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
+            // default: 128-thread CTAs, 12 loads of 128 bits in flight per thread (96 registers, 5 CTAs/SM), 256-byte L2
+            // prefetch granularity
+            default: k_filter_planes<4, 12, 128, 5, 1><<<grid128, 128, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
             }
         }
     } else {
