@@ -227,3 +227,23 @@ def test_count_filter_exactly_at_threshold():
     rows = pp.to_list(out, as_numpy=True)
     assert want[0].rows is not None and rows[0] is not None
     np.testing.assert_array_equal(rows[0], want[0].rows)
+
+
+def test_equal_scores_beyond_one_tranche():
+    """25 200 candidates with IDENTICAL scores: the radix select has to resolve the tranche on the candidate-index bits
+    of the key alone (score range is zero), over several levels."""
+    hyp = oracle.default_hyp(postprocess_bbox=False)
+    heads = [torch.zeros((1, 255, s, s), device="cuda") for s in (80, 40, 20)]
+    rows, want = _check_against_oracle("yolov5", heads, 640, 640, hyp)
+    assert len(rows[0]) == 300
+
+
+def test_two_score_levels_huge_ties():
+    """Half of the candidates share one score, half another: every histogram digit but one is empty."""
+    hyp = oracle.default_hyp(postprocess_bbox=False, max_predictions_per_img=1024)
+    heads = [torch.zeros((2, 255, s, s), device="cuda") for s in (80, 40, 20)]
+    for h in heads:
+        v = h.view(2, 3, 85, h.shape[2], h.shape[3])
+        v[:, :, 4, ::2, :] = 1.5          # objectness of every other row of cells
+        v[:, :, 5 + 7] = 0.75             # one class stands out everywhere
+    _check_against_oracle("yolov5", heads, 640, 640, hyp)
