@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--dist", default="dense", choices=["dense", "sparse", "crowd"])
     ap.add_argument("--pipeline", type=int, default=3, help="0: serial; 1: NMS kernel of batch i overlaps the filter kernel of batch i+1 on a side stream; 2: same, side stream at high priority; 3: two independent lanes (step i entirely on stream i %% 2)")
     ap.add_argument("--lanes", type=int, default=4, help="streams (= batches in flight) of --pipeline 3")
+    ap.add_argument("--graph", type=int, default=0, help="replay one captured CUDA graph (memset + filter + NMS) per step and lane")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-images", type=int, default=2, help="images in the bounded CPU-baseline sample")
     return ap.parse_args()
@@ -318,6 +319,19 @@ def run_ours(args):
 
     step_no = [0]
     lanes = [torch.cuda.Stream(device=dev) for _ in range(n_lanes)] if args.pipeline == 3 else None
+    graphs = None
+    if args.graph and args.pipeline == 3:
+        # one graph per lane: {zero the counters, filter kernel, NMS kernel} with that lane's buffers baked in
+        launch_filter(ptrs, slots[0], stream)
+        launch_nms(ptrs, slots[0], stream)   # first launches outside capture (function attributes, lazy module load)
+        torch.cuda.synchronize()
+        graphs = []
+        for i in range(n_lanes):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=lanes[i], capture_error_mode="thread_local"):
+                launch_filter(ptrs, slots[i], lanes[i])
+                launch_nms(ptrs, slots[i], lanes[i])
+            graphs.append(g)
 
     def step(ev=None, head_ptrs=None):
         head_ptrs = head_ptrs or ptrs
@@ -326,6 +340,17 @@ def run_ours(args):
             # two independent lanes: step i runs filter -> NMS (-> all-gather) in order on stream i % 2, so the NMS
             # kernel of one step overlaps the filter kernel of the next without any cross-stream event
             st = lanes[step_no[0] % n_lanes]
+            if graphs is not None and head_ptrs is ptrs and comm is None:
+                gi = step_no[0] % n_lanes
+                step_no[0] += 1
+                with torch.cuda.stream(st):
+                    if ev:
+                        ev[0].record(st)
+                    graphs[gi].replay()
+                    if ev:
+                        for e_ in ev[1:]:
+                            e_.record(st)
+                return sl
             step_no[0] += 1
             if ev:
                 ev[0].record(st)
@@ -516,7 +541,8 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": algo_bytes,
                          "bytes_per_image": f"N*{n_read_ch}*4 read + M*8 written = {N * n_read_ch * 4} + {m_mean * 8:.0f}",
                          "launch_ms": region_launch_ms},
-            "pipeline": bool(args.pipeline),
+            "pipeline": bool(args.pipeline), "lanes": n_lanes if args.pipeline == 3 else (2 if args.pipeline else 1),
+            "cuda_graph": bool(graphs),
             "stages_ms": {"filter_compact": filt_mean_ms, "select_sort_nms": statistics.mean(nms_ms),
                           "filter_p50": statistics.median(filt_ms), "nms_p50": statistics.median(nms_ms)},
             "survivors_per_image": m_mean,

@@ -247,3 +247,22 @@ def test_two_score_levels_huge_ties():
         v[:, :, 4, ::2, :] = 1.5          # objectness of every other row of cells
         v[:, :, 5 + 7] = 0.75             # one class stands out everywhere
     _check_against_oracle("yolov5", heads, 640, 640, hyp)
+
+
+def test_cuda_graph_capture_replays_with_refilled_heads():
+    from yoloseries_b200 import synth
+    hyp = oracle.default_hyp()
+    pp = _pp("yolov5", hyp)
+    heads = synth.make_heads("yolov5", 2, 320, 320, 80, "crowd", seed=50, device="cuda")
+    replay = pp.capture(heads, 320, 320)
+    for seed, dist_ in ((51, "dense"), (52, "crowd")):
+        fresh = synth.make_heads("yolov5", 2, 320, 320, 80, dist_, seed=seed, device="cuda")
+        for dst, src in zip(heads, fresh):
+            dst.copy_(src)                                   # refill in place: the graph holds the addresses
+        got = pp.to_list(replay(), as_numpy=True)
+        ref = _pp("yolov5", hyp)
+        want = ref.to_list(ref.run(fresh, 320, 320), as_numpy=True)
+        for g, w in zip(got, want):
+            assert (g is None) == (w is None)
+            if g is not None:
+                np.testing.assert_array_equal(g, w)
