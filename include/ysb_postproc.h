@@ -155,6 +155,21 @@ int ysb_nms(const float *d_boxes, const float *d_scores, int64_t m, double iou_t
             int64_t max_keep, void *d_workspace, size_t workspace_bytes, int32_t *d_keep, int32_t *d_keep_cnt,
             void *stream);
 
+/* Soft-NMS (utils/nms.py:68-140; no caller in the reference, float32 GIoU/DIoU/CIoU flavours only -- 'iou' is broken
+ * there).  Repeats: pick the first arg-max, record processed[idx] = its current score, decay every score whose IoU with
+ * it exceeds iou_thr by (1 - iou) (mode 0, linear) or exp(-iou^2 / sigma) (mode 1, exponential), until no score is > 0.
+ * d_processed (m) float32 receives the recorded scores (0 where never picked); the caller thresholds them.
+ * Workspace: m floats.  The loop is capped at max(64, 104*sigma + 2) * m + 1024 picks: in exponential mode a picked box
+ * only decays itself by exp(-1/sigma), so the reference loops until float32 underflow (~104*sigma picks per box), and it
+ * never terminates when a self-IoU does not exceed the threshold. */
+int ysb_soft_nms(const float *d_boxes, const float *d_scores, int64_t m, float iou_thr, int iou_kind, int mode,
+                 float sigma, void *d_workspace, size_t workspace_bytes, float *d_processed, void *stream);
+
+/* "Next" row after the path (val_yolov5.py:140-179, preds_postprocess): undo the letterbox on the kept rows in place.
+ * d_info (batch, 5) float32 = {scale, pad_top, pad_left, org_h, org_w}:  x = clamp((x - pad_left) / scale, 1, org_w - 1),
+ * y = clamp((y - pad_top) / scale, 1, org_h - 1), float32, one rounding per operation. */
+int ysb_undo_letterbox(float *d_dets, const int32_t *d_det_cnt, int batch, int max_det, const float *d_info, void *stream);
+
 /* (n,4) x (m,4) -> (n,m).  kind NUMBA_F64MIX writes float64 (numba_iou), F32 writes float32 (gpu_iou). */
 int ysb_pairwise_iou(const float *d_b1, int64_t n, const float *d_b2, int64_t m, int iou_kind, void *d_out,
                      void *stream);

@@ -135,13 +135,33 @@ def utils_case(utils):
         store[f"tnms_{kind}"] = np.asarray(utils.gpu_nms(b2, sc, kind, 0.45), dtype=np.int32)
     store["tnms_scores"] = sc.numpy()
     store["anchors_64x96"] = utils.GPUAnchor([64, 96])().cpu().numpy()
+    # soft-NMS (utils/nms.py:68-140): dead code in the reference, runs for the giou/diou/ciou flavours with (M,1) scores
+    m = 48
+    sb = b2[:m].clone()
+    ss = torch.from_numpy(rng.uniform(0.05, 1, size=(m, 1)).astype(np.float32))
+    store["soft_boxes"], store["soft_scores"] = sb.numpy(), ss.numpy()
+    for kind in ("giou", "diou", "ciou"):
+        store[f"soft_linear_{kind}"] = utils.gpu_linear_soft_nms(sb, ss, kind, iou_threshold=0.1, thresh=0.4).numpy()
+    store["soft_exp_diou"] = utils.gpu_exponential_soft_nms(sb[:12], ss[:12], "diou", 0.3, sigmma=0.5, thresh=0.001).numpy()
+    # letterbox undo, val_yolov5.py:166-172 (the torch expressions of preds_postprocess on a (K,6) float32 tensor)
+    pred = torch.from_numpy(rng.uniform(-20, 700, size=(40, 6)).astype(np.float32))
+    pred[:, 2:4] = pred[:, 0:2] + torch.from_numpy(rng.uniform(1, 200, size=(40, 2)).astype(np.float32))
+    store["lb_in"] = pred.numpy().copy()
+    scale, pad_top, pad_left, org_h, org_w = 0.7339449541284404, 0, 85, 545, 640
+    pred[:, [0, 2]] -= pad_left
+    pred[:, [1, 3]] -= pad_top
+    pred[:, [0, 1, 2, 3]] /= scale
+    pred[:, [0, 2]] = pred[:, [0, 2]].clamp(1, org_w - 1)
+    pred[:, [1, 3]] = pred[:, [1, 3]].clamp(1, org_h - 1)
+    store["lb_out"] = pred.numpy()
+    store["lb_info"] = np.array([scale, pad_top, pad_left, org_h, org_w], dtype=np.float64)
     return store
 
 
 def main():
     utils, trainer = refharness.import_reference()
     os.makedirs(OUT, exist_ok=True)
-    if len(sys.argv) <= 1:
+    if len(sys.argv) <= 1 or "utils_nms_iou" in sys.argv[1:]:
         np.savez_compressed(os.path.join(OUT, "utils_nms_iou.npz"), **utils_case(utils))
     fcos_thr = {"compute_metric_cls_threshold": 0.2, "compute_metric_iou_threshold": 0.35, "max_predictions_per_img": 100}
     cases = [

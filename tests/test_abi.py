@@ -110,6 +110,15 @@ def test_argument_validation(lib):
     assert lib.ysb_nms_workspace_bytes(-1, ctypes.byref(ws)) == _lib.YSB_ERR_BAD_ARG
     assert lib.ysb_nms_workspace_bytes(10 ** 9, ctypes.byref(ws)) == _lib.YSB_ERR_LIMIT
     assert lib.ysb_status_string(_lib.YSB_ERR_WORKSPACE) == b"workspace too small"
+    # soft-NMS / letterbox entry points validate before touching the device
+    assert lib.ysb_soft_nms(None, None, 0, 0.3, _lib.GIOU, 0, 0.0, None, 0, None, None) == _lib.YSB_OK
+    assert lib.ysb_soft_nms(None, None, 4, 0.3, _lib.GIOU, 0, 0.0, None, 0, None, None) == _lib.YSB_ERR_BAD_ARG
+    assert lib.ysb_soft_nms(1, 1, 4, 0.3, _lib.IOU_NUMBA_F64MIX, 0, 0.0, 1, 16, 1, None) == _lib.YSB_ERR_BAD_ARG
+    assert lib.ysb_soft_nms(1, 1, 4, 0.3, _lib.DIOU, 1, 0.0, 1, 16, 1, None) == _lib.YSB_ERR_BAD_ARG  # sigma must be > 0
+    assert lib.ysb_soft_nms(1, 1, 4, 0.3, _lib.DIOU, 0, 0.0, 1, 15, 1, None) == _lib.YSB_ERR_WORKSPACE
+    assert lib.ysb_undo_letterbox(None, None, 0, 300, None, None) == _lib.YSB_OK
+    assert lib.ysb_undo_letterbox(None, None, 2, 300, None, None) == _lib.YSB_ERR_BAD_ARG
+    assert lib.ysb_undo_letterbox(1, 1, 2, 0, 1, None) == _lib.YSB_ERR_BAD_ARG
     with pytest.raises(ValueError):
         _lib.check(_lib.YSB_ERR_BAD_ARG, "x")
     with pytest.raises(NotImplementedError):

@@ -176,6 +176,70 @@ def test_torch_iou_family_matches_reference():
         gpu_nms(g["tiou_b2"], sc, "iou", 0.45)
 
 
+def test_soft_nms_matches_reference():
+    """utils/nms.py:68-140 through ysb_soft_nms: the reference's own keep masks, and the oracle on a larger set."""
+    from yoloseries_b200.utils import gpu_exponential_soft_nms, gpu_linear_soft_nms
+    g = load_golden("utils_nms_iou")
+    sb, ss = torch.from_numpy(g["soft_boxes"]).cuda(), torch.from_numpy(g["soft_scores"]).cuda()
+    for kind in ("giou", "diou", "ciou"):
+        got = gpu_linear_soft_nms(sb, ss, kind, iou_threshold=0.1, thresh=0.4)
+        assert got.dtype == torch.bool and got.shape == (48,) and got.device == ss.device
+        np.testing.assert_array_equal(got.cpu().numpy(), g[f"soft_linear_{kind}"], err_msg=kind)
+    got = gpu_exponential_soft_nms(sb[:12], ss[:12], "diou", 0.3, sigmma=0.5, thresh=0.001)
+    np.testing.assert_array_equal(got.cpu().numpy(), g["soft_exp_diou"])
+    # CPU tensors in -> CPU mask out, inputs untouched (the reference clones)
+    keep = ss.cpu().clone()
+    got = gpu_linear_soft_nms(sb.cpu(), keep, "giou", iou_threshold=0.1, thresh=0.4)
+    assert got.device.type == "cpu" and torch.equal(keep, ss.cpu())
+    # larger random set against the oracle restatement (more than one 1024-thread sweep per pick)
+    rng = np.random.default_rng(11)
+    m = 2500
+    xy = rng.uniform(0, 400, size=(m, 2)).astype(np.float32)
+    wh = rng.uniform(8, 90, size=(m, 2)).astype(np.float32)
+    boxes = np.concatenate((xy, xy + wh), axis=1)
+    scores = rng.uniform(0.01, 1, size=(m, 1)).astype(np.float32)
+    for kind, thr in (("giou", 0.2), ("diou", 0.3)):
+        ref = oracle.linear_soft_nms(boxes, scores, kind, iou_threshold=thr, thresh=0.3)
+        got = gpu_linear_soft_nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), kind, thr, 0.3)
+        assert 0 < ref.sum() < m
+        np.testing.assert_array_equal(got.cpu().numpy(), ref, err_msg=kind)
+    assert gpu_linear_soft_nms(sb[:0], ss[:0], "giou").shape == (0,)
+    with pytest.raises(ValueError):
+        gpu_linear_soft_nms(sb, ss, "siou")
+    with pytest.raises(AssertionError):
+        gpu_linear_soft_nms(sb, ss[:5], "giou")
+
+
+def test_undo_letterbox_bit_exact():
+    """val_yolov5.py:166-172 through ysb_undo_letterbox: list-level mirror and the in-place device hook."""
+    from yoloseries_b200.engine import DetectionBuffers, PostProcessor, preds_postprocess
+    g = load_golden("utils_nms_iou")
+    scale, pad_top, pad_left, org_h, org_w = g["lb_info"].tolist()
+    info = dict(scale=scale, pad_top=int(pad_top), pad_left=int(pad_left), pad_bottom=0, pad_right=0,
+                org_shape=(int(org_h), int(org_w)))
+    other = dict(scale=0.5, pad_top=12, pad_left=0, pad_bottom=12, pad_right=0, org_shape=(720, 1280))
+    rows = torch.from_numpy(g["lb_in"])
+    out = preds_postprocess([rows, None, rows[:7], rows[:0]], [info, info, other, info])
+    np.testing.assert_array_equal(out[0], g["lb_out"])
+    assert out[1] is None and out[3].shape == (0, 6)
+    np.testing.assert_array_equal(out[2], oracle.undo_letterbox(g["lb_in"][:7], 0.5, 12, 0, 720, 1280))
+    np.testing.assert_array_equal(rows.numpy(), g["lb_in"])  # caller's rows untouched
+    # device hook on DetectionBuffers: rows beyond the count are left alone
+    buf = DetectionBuffers(2, 64, torch.device("cuda"))
+    buf.dets.zero_()
+    buf.dets[0, :40] = rows.cuda()
+    buf.dets[1, :40] = rows.cuda()
+    buf.det_cnt.copy_(torch.tensor([40, 5], dtype=torch.int32))
+    pp = PostProcessor("yolov5", oracle.default_hyp())
+    pp.undo_letterbox(buf, [info, info])
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(buf.dets[0, :40].cpu().numpy(), g["lb_out"])
+    np.testing.assert_array_equal(buf.dets[1, :5].cpu().numpy(), g["lb_out"][:5])
+    np.testing.assert_array_equal(buf.dets[1, 5:40].cpu().numpy(), g["lb_in"][5:])
+    with pytest.raises(ValueError):
+        pp.undo_letterbox(buf, [info])
+
+
 def test_gather_detections_single_process_identity():
     from yoloseries_b200.dist import gather_detections
     d = torch.rand(4, 10, 6, device="cuda")

@@ -115,3 +115,36 @@ def test_gpu_iou_f32_matches_reference():
 def test_retinanet_anchors_bit_exact():
     g = load_golden("utils_nms_iou")
     np.testing.assert_array_equal(oracle.retinanet_anchors(64, 96), g["anchors_64x96"])
+
+
+def test_torch_iou_flavours_match_reference():
+    """oracle/softnms.py float32 GIoU / DIoU / CIoU vs the reference's torch outputs (utils/bbox_tools.py:193-339)."""
+    g = load_golden("utils_nms_iou")
+    b1, b2 = g["tiou_b1"], g["tiou_b2"]
+    np.testing.assert_array_equal(oracle.giou(b1, b2), g["tiou_giou"])
+    np.testing.assert_array_equal(oracle.diou(b1, b2), g["tiou_diou"])
+    assert np.abs(oracle.ciou(b1, b2) - g["tiou_ciou"]).max() <= 1e-6  # atan is not correctly rounded in either library
+    np.testing.assert_array_equal(oracle.giou(b1[:1], b2), g["tiou_giou_row"])
+    np.testing.assert_array_equal(oracle.diou(b1[:1], b2), g["tiou_diou_row"])
+
+
+def test_soft_nms_masks_match_reference():
+    """utils/nms.py:68-140: the keep masks of the reference on 48 (linear) / 12 (exponential) boxes."""
+    g = load_golden("utils_nms_iou")
+    sb, ss = g["soft_boxes"], g["soft_scores"]
+    for kind in ("giou", "diou", "ciou"):
+        ref = g[f"soft_linear_{kind}"]
+        assert 0 < ref.sum() < ref.size  # a discriminating case
+        np.testing.assert_array_equal(oracle.linear_soft_nms(sb, ss, kind, iou_threshold=0.1, thresh=0.4), ref)
+    got = oracle.exponential_soft_nms(sb[:12], ss[:12], "diou", 0.3, sigma=0.5, thresh=0.001)
+    np.testing.assert_array_equal(got, g["soft_exp_diou"])
+    assert not got.any()  # the reference's exponential variant re-picks until underflow: nothing survives
+
+
+def test_undo_letterbox_bit_exact():
+    """val_yolov5.py:166-172."""
+    g = load_golden("utils_nms_iou")
+    scale, pad_top, pad_left, org_h, org_w = g["lb_info"].tolist()
+    got = oracle.undo_letterbox(g["lb_in"], scale, pad_top, pad_left, org_h, org_w)
+    np.testing.assert_array_equal(got, g["lb_out"])
+    assert got[:, :4].min() >= 1 and got[:, [0, 2]].max() <= org_w - 1 and got[:, [1, 3]].max() <= org_h - 1

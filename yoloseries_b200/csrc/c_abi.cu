@@ -24,6 +24,10 @@ cudaError_t launch_elementwise_iou(const float *b1, int64_t n1, const float *b2,
 cudaError_t debug_k2_timing(long long *host_out);
 #endif
 
+cudaError_t launch_soft_nms(const float *boxes, const float *scores, int64_t m, float thr, int kind, int mode, float sigma,
+                            void *ws, float *processed, cudaStream_t stream);
+cudaError_t launch_undo_letterbox(float *dets, const int32_t *cnt, int batch, int max_det, const float *info, cudaStream_t stream);
+
 static thread_local int g_last_cuda_error = 0;
 
 static int cuda_status(cudaError_t e)
@@ -347,6 +351,25 @@ int ysb_nms(const float *d_boxes, const float *d_scores, int64_t m, double iou_t
     if (workspace_bytes < array_nms_workspace_bytes(m)) return YSB_ERR_WORKSPACE;
     return cuda_status(launch_array_nms(d_boxes, d_scores, m, iou_thr, cmp, iou_kind, max_keep, d_workspace, d_keep,
                                         d_keep_cnt, static_cast<cudaStream_t>(stream)));
+}
+
+int ysb_soft_nms(const float *d_boxes, const float *d_scores, int64_t m, float iou_thr, int iou_kind, int mode,
+                 float sigma, void *d_workspace, size_t workspace_bytes, float *d_processed, void *stream)
+{
+    if (m < 0 || (m > 0 && (!d_boxes || !d_scores || !d_workspace || !d_processed))) return YSB_ERR_BAD_ARG;
+    if (iou_kind != YSB_GIOU && iou_kind != YSB_DIOU && iou_kind != YSB_CIOU && iou_kind != YSB_IOU_F32) return YSB_ERR_BAD_ARG;
+    if (mode != 0 && mode != 1) return YSB_ERR_BAD_ARG;
+    if (mode == 1 && !(sigma > 0.0f)) return YSB_ERR_BAD_ARG;
+    if (m > YSB_MAX_CANDIDATES) return YSB_ERR_LIMIT;
+    if (workspace_bytes < sizeof(float) * static_cast<size_t>(m)) return YSB_ERR_WORKSPACE;
+    return cuda_status(launch_soft_nms(d_boxes, d_scores, m, iou_thr, iou_kind, mode, sigma, d_workspace, d_processed,
+                                       static_cast<cudaStream_t>(stream)));
+}
+
+int ysb_undo_letterbox(float *d_dets, const int32_t *d_det_cnt, int batch, int max_det, const float *d_info, void *stream)
+{
+    if (batch < 0 || max_det <= 0 || (batch > 0 && (!d_dets || !d_det_cnt || !d_info))) return YSB_ERR_BAD_ARG;
+    return cuda_status(launch_undo_letterbox(d_dets, d_det_cnt, batch, max_det, d_info, static_cast<cudaStream_t>(stream)));
 }
 
 int ysb_pairwise_iou(const float *d_b1, int64_t n, const float *d_b2, int64_t m, int iou_kind, void *d_out, void *stream)

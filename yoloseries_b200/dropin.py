@@ -27,7 +27,9 @@ def install(patch_evaluators=True, patch_utils=True):
     if ref_utils is None or ref_trainer is None:
         raise RuntimeError("import the reference's `utils` and `trainer` packages before dropin.install()")
     if patch_utils:
-        for name, fn in (("numba_nms", _nms.numba_nms), ("gpu_nms", _nms.gpu_nms), ("numba_iou", _bbox.numba_iou)):
+        for name, fn in (("numba_nms", _nms.numba_nms), ("gpu_nms", _nms.gpu_nms), ("numba_iou", _bbox.numba_iou),
+                         ("gpu_linear_soft_nms", _nms.gpu_linear_soft_nms),
+                         ("gpu_exponential_soft_nms", _nms.gpu_exponential_soft_nms)):
             setattr(ref_utils, name, fn)
             for sub in ("utils.nms", "utils.bbox_tools"):
                 mod = sys.modules.get(sub)

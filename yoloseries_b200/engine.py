@@ -128,6 +128,40 @@ def make_params(family, hyp, batch, img_h, img_w, level_shapes=None, anchors=Non
     return p
 
 
+def letterbox_table(info):
+    """list of the reference's per-image info dicts -> (b, 5) rows {scale, pad_top, pad_left, org_h, org_w}."""
+    return [[float(d["scale"]), float(d["pad_top"]), float(d["pad_left"]), float(d["org_shape"][0]),
+             float(d["org_shape"][1])] for d in info]
+
+
+def preds_postprocess(outputs, info):
+    """val_yolov5.py:164-177 for an evaluator's output list: list[Tensor(K,6) | None] -> list[ndarray(K,6) | None].
+
+    (The image half of the reference's method -- un-padding and resizing the input picture for drawing -- is
+    visualisation and stays with the caller.)  Rows are staged to the device, mapped by ysb_undo_letterbox, and read back.
+    """
+    if len(outputs) != len(info):
+        raise ValueError(f"need one info dict per image: {len(info)} != {len(outputs)}")
+    if not outputs:
+        return []
+    if not torch.cuda.is_available():
+        raise RuntimeError("yoloseries_b200 needs a CUDA device: the engine has no CPU fallback")
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    kmax = max([1] + [int(o.shape[0]) for o in outputs if o is not None])
+    host = torch.zeros((len(outputs), kmax, 6), dtype=torch.float32)
+    cnt = torch.tensor([(-1 if o is None else int(o.shape[0])) for o in outputs], dtype=torch.int32)
+    for i, o in enumerate(outputs):
+        if o is not None and o.shape[0]:
+            host[i, : o.shape[0]] = torch.as_tensor(o, dtype=torch.float32).reshape(-1, 6)
+    dets, dcnt = host.to(dev), cnt.to(dev)
+    table = torch.tensor(letterbox_table(info), dtype=torch.float32).to(dev)
+    _lib.check(lib.ysb_undo_letterbox(dets.data_ptr(), dcnt.data_ptr(), len(outputs), kmax, table.data_ptr(),
+                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "ysb_undo_letterbox")
+    back = dets.cpu().numpy()
+    return [None if c < 0 else back[i, :c].copy() for i, c in enumerate(cnt.tolist())]
+
+
 class DetectionBuffers:
     """Per-call device outputs: rows (b, max_det, 6), candidate indices (b, max_det), counts (b)."""
 
@@ -257,6 +291,22 @@ class PostProcessor:
                                                    slots, counts.data_ptr(), self._stream()),
                    "ysb_filter_candidates")
         return keys, counts
+
+    def undo_letterbox(self, out, info):
+        """The box part of val_yolov5.py:140-179 (preds_postprocess) on the kept rows, in place, before the D2H copy.
+
+        ``info``: per image the reference's dict (``scale``, ``pad_top``, ``pad_left``, ``org_shape`` = (h, w)).
+        x = clamp((x - pad_left) / scale, 1, org_w - 1), y likewise with pad_top / org_h; float32, op by op.
+        """
+        if out.det_cnt.numel() == 0:
+            return out
+        if len(info) != out.det_cnt.numel():
+            raise ValueError(f"need one info dict per image: {len(info)} != {out.det_cnt.numel()}")
+        table = torch.tensor(letterbox_table(info), dtype=torch.float32).to(out.dets.device, non_blocking=True)
+        _lib.check(self._lib.ysb_undo_letterbox(out.dets.data_ptr(), out.det_cnt.data_ptr(), out.dets.shape[0],
+                                                out.dets.shape[1], table.data_ptr(), self._stream()),
+                   "ysb_undo_letterbox")
+        return out
 
     @staticmethod
     def to_list(out, as_numpy=False, with_index=False):
