@@ -14,6 +14,10 @@
  *   ysb_select_nms        class offset + utils.numba_nms   trainer/eval_yolov5.py:293-316, utils/nms.py:10-27,
  *                         + max_det + postprocess_bbox     utils/bbox_tools.py:12-35
  *   ysb_postprocess       XEvaluator.__call__ minus model  trainer/eval_yolov5.py:30-42
+ *   ysb_postprocess_tta   the same with hyp['use_tta']     trainer/eval_yolov5.py:30-42 + 152-179 (test_time_augmentation)
+ *   ysb_decode_into       one pass of test_time_augmentation (decode + scale/flip undo + concat slot)
+ *   ysb_soft_nms          utils.gpu_*_soft_nms             utils/nms.py:68-140
+ *   ysb_undo_letterbox    box half of preds_postprocess    val_yolov5.py:166-172
  *   ysb_nms               utils.numba_nms / utils.gpu_nms  utils/nms.py:10-27 / 30-65
  *   ysb_pairwise_iou      utils.numba_iou / utils.gpu_iou  utils/bbox_tools.py:12-35 / 164-190
  *   ysb_elementwise_iou   utils.gpu_Giou/gpu_DIoU/gpu_CIoU utils/bbox_tools.py:193-339
@@ -35,9 +39,10 @@
 extern "C" {
 #endif
 
-#define YSB_ABI_VERSION 1
+#define YSB_ABI_VERSION 2
 #define YSB_MAX_LEVELS 8
 #define YSB_MAX_ANCHORS 9
+#define YSB_MAX_PASSES 4             /* test-time-augmentation passes merged by ysb_postprocess_tta */
 #define YSB_MAX_DET_LIMIT 1024      /* max_det upper bound (kept list lives in shared memory) */
 #define YSB_MAX_CANDIDATES 4194303  /* candidate index must fit 22 bits of the sort key */
 #define YSB_MAX_CLASSES 1024        /* class id must fit 10 bits of the sort key */
@@ -111,6 +116,14 @@ typedef struct ysb_params {
     int32_t thresh_with_ctr;   /* FCOS thresh_with_ctr */
     int32_t decoded_rows;      /* DECODED_ROWS input only: rows per image when it is not the family's own N
                                   (e.g. the concatenation of three TTA passes, eval_yolov5.py:152-179); 0 = N */
+    /* Test-time-augmentation undo of ONE pass (test_time_augmentation, eval_yolov5.py:152-179, eval_yolov8.py:40-73,
+     * eval_retinanet.py:148-182, eval_fcos.py:90-123), applied to the four box columns right after the decode, RAW_HEADS
+     * input only:  box /= tta_scale (float32 division; 0 or 1 = off), then for tta_flip == 2 (picture flipped along h)
+     * cy = tta_img_h - cy   or   (y1, y2) = (tta_img_h - y2, tta_img_h - y1);  tta_flip == 3 (along w) likewise with x and
+     * tta_img_w.  tta_img_h/w are the size of the UN-augmented input (img_h/img_w above describe the padded pass). */
+    float tta_scale;
+    int32_t tta_flip;          /* 0 none, 2, 3: the reference's flip_axis values */
+    int32_t tta_img_h, tta_img_w;
 } ysb_params;
 
 int ysb_abi_version(void);
@@ -123,6 +136,12 @@ int ysb_num_candidates(const ysb_params *p, int64_t *n_out, int32_t *row_width_o
 
 /* do_inference: raw heads -> d_decoded (batch, N, C') float32, reference row layout per family. */
 int ysb_decode(const ysb_params *p, const void *const *d_heads, int num_heads, float *d_decoded, void *stream);
+
+/* The same decode written into a larger tensor: d_decoded is (batch, rows_total, C') and this pass fills rows
+ * [row_offset, row_offset + N) of every image -- with the tta_* undo of the params applied, three calls build the merged
+ * tensor of test_time_augmentation (eval_yolov5.py:179, torch.cat(aug_preds, dim=1)) without an intermediate copy. */
+int ysb_decode_into(const ysb_params *p, const void *const *d_heads, int num_heads, float *d_decoded, int64_t rows_total,
+                    int64_t row_offset, void *stream);
 
 /* Filter + class pick + compaction.  d_keys: (batch, key_capacity) uint64 sort keys
  *   key = score_bits << 32 | (YSB_MAX_CANDIDATES - cand) << 10 | (1023 - cls)
@@ -145,6 +164,17 @@ int ysb_select_nms(const ysb_params *p, const void *const *d_heads, int num_head
 int ysb_postprocess_workspace_bytes(const ysb_params *p, size_t *bytes_out);
 int ysb_postprocess(const ysb_params *p, const void *const *d_heads, int num_heads, void *d_workspace,
                     size_t workspace_bytes, float *d_dets, int32_t *d_det_idx, int32_t *d_det_cnt, void *stream);
+
+/* XEvaluator.__call__ with hyp['use_tta'] (eval_yolov5.py:30-42 + 152-179) minus the model forwards: num_passes
+ * parameter sets (same family / thresholds / batch, own geometry and tta_* undo each) and their raw heads, concatenated in
+ * d_heads (heads_per_pass[i] pointers for pass i).  Candidate index space = the concatenation of the passes in order, as
+ * in the reference's merged tensor; the merged (b, sum N_i, C') tensor is never materialised: every pass runs the filter
+ * kernel on its own heads appending to one key list per image, and ONE selection/NMS kernel decodes the boxes of the
+ * candidates it visits from the pass they belong to.  Outputs as ysb_select_nms (d_det_idx = merged candidate index). */
+int ysb_postprocess_tta_workspace_bytes(const ysb_params *passes, int num_passes, size_t *bytes_out);
+int ysb_postprocess_tta(const ysb_params *passes, int num_passes, const void *const *d_heads, const int32_t *heads_per_pass,
+                        void *d_workspace, size_t workspace_bytes, float *d_dets, int32_t *d_det_idx,
+                        int32_t *d_det_cnt, void *stream);
 
 /* Greedy NMS over one explicit box/score array (utils.numba_nms / utils.gpu_nms).
  *   d_boxes (m,4) float32, d_scores (m) float32 >= 0 (zero scores are never kept, utils/nms.py:16)

@@ -92,6 +92,51 @@ def evaluator_case(trainer, family, dist, img, batch, seed, C=80, **hyp_over):
     return store
 
 
+def tta_case(trainer, family, img_h, img_w, batch, seed, C=4, **hyp_over):
+    """use_tta=True: the reference's own test_time_augmentation + numba_nms over three passes (scale 1 / 0.83 / 0.67,
+    flip none / h / w).  The stand-in model hands out a different seeded head set on every forward."""
+    from collections import OrderedDict
+
+    hyp = refharness.reference_hyp((img_h, img_w), num_class=C, use_tta=True, **hyp_over)
+    sets = [synth.make_heads(family, batch, img_h, img_w, C, "dense", seed + k, "cpu") for k in range(3)]
+    calls = {"n": 0}
+
+    def model(x):
+        assert tuple(x.shape[2:]) == (img_h, img_w), x.shape  # multiples of 32: every pass is padded back to the input size
+        heads = _clone(sets[calls["n"] % 3])
+        calls["n"] += 1
+        if family in ("yolov7", "yolox", "yolov8"):
+            return OrderedDict((f"p{i}", h) for i, h in enumerate(heads))
+        return heads
+
+    anchors = torch.tensor(synth.V5_ANCHORS_PX)
+    cls = {"yolov5": "YOLOV5Evaluator", "yolov7": "YOLOV7Evaluator", "yolox": "YOLOXEvaluator", "yolov8": "YOLOV8Evaluator",
+           "retinanet": "RetinaNetEvaluator", "retinanet_exp": "RetinaNetEvaluatorExperiment", "fcos": "FCOSEvaluator"}[family]
+    args = (model, anchors, hyp) if family in ("yolov5", "yolov7") else (model, hyp)
+    ev = getattr(trainer, cls)(*args, compute_metric=True)
+    # distinguishable picture content so that a wrong flip/scale of the INPUT would not go unnoticed by a real model;
+    # the stand-in model ignores it
+    dummy = torch.rand(batch, 3, img_h, img_w, generator=torch.Generator().manual_seed(seed))
+    merged, per_pass = ev.test_time_augmentation(dummy)
+    assert calls["n"] == 3
+    outs = ev.numba_nms(merged.clone())
+    rows, cnt = _pack_outputs(outs)
+    # __call__ must agree with the two-step form
+    again = ev(dummy)
+    for a, b in zip(again, outs):
+        assert (a is None and b is None) or np.array_equal(a.numpy(), b)
+    store = {"merged": merged.numpy().astype(np.float32), "rows": rows, "counts": cnt}
+    assert calls["n"] % 3 == 0
+    for k in range(3):
+        _flat_np(f"p{k}_head", sets[k], store)
+        # the pass's decoded tensor BEFORE the scale/flip undo (the stand-in model hands out set k again)
+        store[f"p{k}_decoded"] = ev.do_inference(dummy).numpy().astype(np.float32)
+    meta = dict(family=family, dist="dense", img=img_h, img_h=img_h, img_w=img_w, batch=batch, seed=seed, num_class=C)
+    meta.update({k: v for k, v in hyp.items() if isinstance(v, (int, float, bool, str))})
+    store["meta"] = np.array(repr(meta))
+    return store
+
+
 def utils_case(utils):
     """utils/nms.py + utils/bbox_tools.py on random and hand-made boxes."""
     rng = np.random.default_rng(7)
@@ -195,6 +240,22 @@ def main():
         ("fcos_multilabel", "fcos", "dense", 128, 1, 76, 4, dict(fcos_thr, mutil_label=True)),
     ]
     only = set(sys.argv[1:])
+    tta_cases = [
+        ("tta_yolov5", "yolov5", 64, 96, 2, 81, 4, {}),
+        ("tta_yolov7", "yolov7", 64, 96, 1, 82, 4, {}),
+        ("tta_yolox", "yolox", 64, 96, 2, 83, 4, {}),
+        ("tta_yolov8", "yolov8", 64, 96, 1, 84, 4, {}),
+        ("tta_retinanet", "retinanet", 64, 96, 1, 85, 4, {}),
+        ("tta_fcos", "fcos", 128, 128, 1, 86, 4, fcos_thr),
+    ]
+    for name, family, img_h, img_w, batch, seed, C, over in tta_cases:
+        if only and name not in only:
+            continue
+        store = tta_case(trainer, family, img_h, img_w, batch, seed, C, **over)
+        path = os.path.join(OUT, f"{name}.npz")
+        np.savez_compressed(path, **store)
+        print(f"{name:24s} rows={store['merged'].shape[1]:6d} counts={store['counts'].tolist()} "
+              f"{os.path.getsize(path) / 1024:.0f} KiB")
     for name, family, dist, img, batch, seed, C, over in cases:
         if only and name not in only:
             continue

@@ -33,7 +33,8 @@ def pytest_collection_modifyitems(config, items):
 
 def golden_names(prefix=""):
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    return [n for n in names if n.startswith(prefix) and n != "utils_nms_iou"]
+    # tta_* fixtures hold three head sets and the merged tensor: asked for explicitly with golden_names("tta_")
+    return [n for n in names if n.startswith(prefix) and n != "utils_nms_iou" and (prefix or not n.startswith("tta_"))]
 
 
 def load_golden(name):
@@ -57,6 +58,13 @@ def golden_heads(data):
         return tuple(groups)
     ks = sorted(keys, key=lambda s: int(s.split("_")[-1]))
     return [data[k] for k in ks]
+
+
+def tta_pass_heads(data, k):
+    """Head structure of pass k of a tta_* fixture (keys p{k}_head_...)."""
+    sub = {key[len(f"p{k}_"):]: v for key, v in data.items() if key.startswith(f"p{k}_head")}
+    sub["meta"] = data["meta"]
+    return golden_heads(sub)
 
 
 def hyp_from_meta(meta):

@@ -149,3 +149,39 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(d, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{f} imports the oracle"
+
+
+def test_tta_entry_points_validate_on_the_host(lib):
+    """ysb_postprocess_tta / ysb_decode_into: pass lists are checked before anything touches the device."""
+    from yoloseries_b200 import _lib
+    from yoloseries_b200._lib import YsbParams
+    base = _v5_params()
+    ws1, ws3 = ctypes.c_size_t(), ctypes.c_size_t()
+    assert lib.ysb_postprocess_workspace_bytes(ctypes.byref(base), ctypes.byref(ws1)) == 0
+
+    def passes(*ps):
+        return (YsbParams * len(ps))(*ps)
+
+    p1, p2 = _v5_params(), _v5_params()
+    p1.tta_scale, p1.tta_flip, p1.tta_img_h, p1.tta_img_w = 0.83, 2, 640, 640
+    p2.tta_scale, p2.tta_flip, p2.tta_img_h, p2.tta_img_w = 0.67, 3, 640, 640
+    arr = passes(base, p1, p2)
+    assert lib.ysb_postprocess_tta_workspace_bytes(arr, 3, ctypes.byref(ws3)) == 0
+    assert ws3.value >= 3 * 4 * 25200 * 8                      # one key slot per candidate of every pass
+    assert lib.ysb_postprocess_tta_workspace_bytes(arr, 0, ctypes.byref(ws3)) == _lib.YSB_ERR_BAD_ARG
+    assert lib.ysb_postprocess_tta_workspace_bytes(arr, 5, ctypes.byref(ws3)) == _lib.YSB_ERR_BAD_ARG
+    assert lib.ysb_postprocess_tta_workspace_bytes(None, 3, ctypes.byref(ws3)) == _lib.YSB_ERR_BAD_ARG
+    bad = _v5_params()
+    bad.tta_flip = 1                                           # the reference flips along dims 2 or 3 only
+    assert lib.ysb_postprocess_tta_workspace_bytes(passes(base, bad), 2, ctypes.byref(ws3)) == _lib.YSB_ERR_BAD_ARG
+    other = _v5_params()
+    other.iou_thr = 0.5                                        # one evaluator, one hyp: thresholds must agree
+    assert lib.ysb_postprocess_tta_workspace_bytes(passes(base, other), 2, ctypes.byref(ws3)) == _lib.YSB_ERR_BAD_ARG
+    dec = _v5_params()
+    dec.input_kind = _lib.INPUT_DECODED_ROWS                   # decoded rows already carry their undo
+    assert lib.ysb_postprocess_tta_workspace_bytes(passes(base, dec), 2, ctypes.byref(ws3)) == _lib.YSB_ERR_BAD_ARG
+    dec.tta_flip = 2
+    n = ctypes.c_int64()
+    assert lib.ysb_num_candidates(ctypes.byref(dec), ctypes.byref(n), None) == _lib.YSB_ERR_BAD_ARG
+    assert lib.ysb_postprocess_tta(arr, 3, None, None, None, 0, None, None, None, None) == _lib.YSB_ERR_BAD_ARG
+    assert lib.ysb_decode_into(ctypes.byref(base), None, 3, None, 25200, 0, None) == _lib.YSB_ERR_BAD_ARG

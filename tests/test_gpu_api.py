@@ -97,24 +97,6 @@ def test_evaluator_call_contract(name):
             np.testing.assert_array_equal(o.numpy(), s)
 
 
-def test_tta_path_matches_oracle():
-    """use_tta=True: three scaled/flipped passes concatenated (75% more rows than N) through the decoded-rows kernels."""
-    g = load_golden("yolov5_crowd")
-    ev = _make_evaluator(g, use_tta=True)
-    img = g["meta"]["img"]
-    # the fake model ignores its input, so feed tensors of the size each pass expects: use the merged tensor directly
-    dec = ev._pp.decode(_cuda(golden_heads(g)), img, img)
-    merged = torch.cat([dec, dec / 0.83, dec.flip(1)], dim=1).contiguous()
-    outs = ev.numba_nms(merged)
-    hyp = oracle.default_hyp(num_class=g["meta"]["num_class"])
-    want = oracle.evaluator_nms("yolov5", merged.cpu().numpy(), hyp)
-    for o, w in zip(outs, want):
-        if w.rows is None:
-            assert o is None
-        else:
-            np.testing.assert_array_equal(o, w.rows)
-
-
 def test_utils_numba_nms_and_iou_match_reference():
     from yoloseries_b200.utils import numba_iou, numba_nms
     g = load_golden("utils_nms_iou")

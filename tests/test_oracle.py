@@ -3,11 +3,14 @@ import numpy as np
 import pytest
 
 import oracle
-from conftest import v8_box_scale, close_rel, golden_heads, golden_names, hyp_from_meta, load_golden
+from conftest import (v8_box_scale, close_rel, golden_heads, golden_names, hyp_from_meta, load_golden,
+                      tta_pass_heads)
 
 
 def _decode(family, heads, meta):
     C, img = meta["num_class"], meta["img"]
+    if family in ("retinanet", "retinanet_exp") and "img_w" in meta:
+        return oracle.decode_retinanet(heads[0], heads[1], meta["img_h"], meta["img_w"])
     if family == "yolov5":
         return oracle.decode_yolov5(heads, num_class=C)
     if family == "yolov7":
@@ -148,3 +151,44 @@ def test_undo_letterbox_bit_exact():
     got = oracle.undo_letterbox(g["lb_in"], scale, pad_top, pad_left, org_h, org_w)
     np.testing.assert_array_equal(got, g["lb_out"])
     assert got[:, :4].min() >= 1 and got[:, [0, 2]].max() <= org_w - 1 and got[:, [1, 3]].max() <= org_h - 1
+
+
+@pytest.mark.parametrize("name", golden_names("tta_"))
+def test_tta_merge_and_rows_match_reference(name):
+    """test_time_augmentation (eval_yolov5.py:152-179 & siblings): decode of every pass + scale/flip undo + concat, then
+    the evaluator's numba_nms over the merged tensor, against the reference's own merged tensor and rows."""
+    g = load_golden(name)
+    meta = g["meta"]
+    fam, C = meta["family"], meta["num_class"]
+    passes = [_decode(fam, tta_pass_heads(g, k), meta) for k in range(3)]
+    merged = oracle.tta_merge(fam, passes, meta["img_h"], meta["img_w"], C)
+    ref = g["merged"]
+    assert merged.shape == ref.shape
+    b0 = oracle.tta.box_col(fam, C)
+    other = [c for c in range(ref.shape[2]) if not b0 <= c < b0 + 4]
+    assert close_rel(merged[..., other], ref[..., other], 1e-5).all()
+    if fam == "yolov8":      # cancellation in (g - l) * s, see test_decode_matches_reference; bound by the operands' size
+        bound = 1e-5 * (max(meta["img_h"], meta["img_w"]) + 16 * 32) / min(oracle.TTA_SCALES)
+        assert np.abs(merged[..., :4] - ref[..., :4]).max() <= bound
+    elif fam.startswith("retinanet"):  # round_() flips of a 1-ulp exp difference, scaled by the pass's 1/s
+        bad = ~close_rel(merged[..., b0:b0 + 4], ref[..., b0:b0 + 4], 1e-5)
+        assert bad.sum() <= 4 and np.all(np.abs(merged[..., b0:b0 + 4][bad] - ref[..., b0:b0 + 4][bad]) <= 1.0 / 0.67 + 1e-3)
+    else:
+        assert close_rel(merged[..., b0:b0 + 4], ref[..., b0:b0 + 4], 1e-5).all()
+    # the undo + concat alone, on the reference's own per-pass decoded tensors: bit-exact (float32 true division)
+    exact = oracle.tta_merge(fam, [g[f"p{k}_decoded"] for k in range(3)], meta["img_h"], meta["img_w"], C)
+    np.testing.assert_array_equal(exact, ref)
+    # rows: numba_nms over the reference's merged tensor, bit-exact (RetinaNet merged boxes 1e-5)
+    res = oracle.evaluator_nms(fam, ref, hyp_from_meta(meta), full_nms=True)
+    for i, r in enumerate(res):
+        cnt = int(g["counts"][i])
+        if cnt < 0:
+            assert r.rows is None
+            continue
+        want = g["rows"][i, :cnt]
+        assert r.rows.shape == want.shape
+        if fam.startswith("retinanet"):
+            np.testing.assert_array_equal(r.rows[:, 4:], want[:, 4:])
+            assert close_rel(r.rows[:, :4], want[:, :4], 1e-5).all()
+        else:
+            np.testing.assert_array_equal(r.rows, want)

@@ -23,6 +23,8 @@ IOU_NUMBA_F64MIX, IOU_F32, GIOU, DIOU, CIOU = range(5)
 IOU_KIND_IDS = {"numba": IOU_NUMBA_F64MIX, "iou": IOU_F32, "giou": GIOU, "diou": DIOU, "ciou": CIOU}
 CMP_GE, CMP_GT = 0, 1
 
+ABI_VERSION = 2
+YSB_MAX_PASSES = 4
 YSB_OK, YSB_ERR_BAD_ARG, YSB_ERR_UNSUPPORTED, YSB_ERR_WORKSPACE, YSB_ERR_CUDA, YSB_ERR_LIMIT = 0, -1, -2, -3, -4, -5
 
 
@@ -55,6 +57,10 @@ class YsbParams(ctypes.Structure):
         ("pre_nms_topk", ctypes.c_int32),
         ("thresh_with_ctr", ctypes.c_int32),
         ("decoded_rows", ctypes.c_int32),
+        ("tta_scale", ctypes.c_float),
+        ("tta_flip", ctypes.c_int32),
+        ("tta_img_h", ctypes.c_int32),
+        ("tta_img_w", ctypes.c_int32),
     ]
 
 
@@ -87,6 +93,13 @@ _SIGNATURES = {
     "ysb_nms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_int,
                                ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
                                ctypes.c_void_p, ctypes.c_void_p]),
+    "ysb_decode_into": (ctypes.c_int, [ctypes.POINTER(YsbParams), ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
+                                       ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
+    "ysb_postprocess_tta_workspace_bytes": (ctypes.c_int, [ctypes.POINTER(YsbParams), ctypes.c_int,
+                                                           ctypes.POINTER(ctypes.c_size_t)]),
+    "ysb_postprocess_tta": (ctypes.c_int, [ctypes.POINTER(YsbParams), ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
+                                           ctypes.POINTER(ctypes.c_int32), ctypes.c_void_p, ctypes.c_size_t,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "ysb_soft_nms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_float, ctypes.c_int, ctypes.c_int,
                                     ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
     "ysb_undo_letterbox": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
@@ -112,7 +125,7 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.ysb_abi_version() != 1:
+        if lib.ysb_abi_version() != ABI_VERSION:
             raise ImportError("libysb_postproc.so ABI version mismatch")
         _lib = lib
     return _lib

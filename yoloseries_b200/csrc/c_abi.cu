@@ -9,10 +9,14 @@
 #include "ysb_internal.cuh"
 
 namespace ysb {
-cudaError_t launch_filter(const Plan &P, int vec, uint64_t *d_keys, int64_t key_cap, int32_t *d_counts, cudaStream_t stream);
+cudaError_t launch_filter(const Plan &P, int vec, uint64_t *d_keys, int64_t key_cap, int32_t *d_counts, cudaStream_t stream,
+                          bool zero_counts);
 cudaError_t launch_select_nms(const Plan &P, const uint64_t *d_keys, int64_t key_cap, const int32_t *d_counts,
                               float *d_dets, int32_t *d_det_idx, int32_t *d_det_cnt, cudaStream_t stream);
-cudaError_t launch_decode(const Plan &P, float *d_out, cudaStream_t stream);
+cudaError_t launch_select_nms_tta(const Plan &P, const ExtraPasses &X, const uint64_t *d_keys, int64_t key_cap,
+                                  const int32_t *d_counts, float *d_dets, int32_t *d_det_idx, int32_t *d_det_cnt,
+                                  cudaStream_t stream);
+cudaError_t launch_decode(const Plan &P, float *d_out, int64_t rows_total, int64_t row_offset, cudaStream_t stream);
 cudaError_t launch_array_nms(const float *d_boxes, const float *d_scores, int64_t m, double iou_thr, int cmp, int iou_kind,
                              int64_t max_keep, void *ws, int32_t *d_keep, int32_t *d_keep_cnt, cudaStream_t stream);
 size_t array_nms_workspace_bytes(int64_t m);
@@ -98,6 +102,15 @@ static int build_plan(const ysb_params *p, const void *const *d_heads, int num_h
     P.obj_col = -1;
     P.multi_label = p->multi_label != 0;
     P.multi_strict = p->family == YSB_FCOS;  // eval_fcos.py:247 uses '>', the other families '>='
+    // test-time-augmentation undo of this pass (raw heads only: decoded rows already carry it)
+    if (p->tta_flip != 0 && p->tta_flip != 2 && p->tta_flip != 3) return YSB_ERR_BAD_ARG;
+    if (p->tta_scale < 0.0f || p->tta_scale != p->tta_scale) return YSB_ERR_BAD_ARG;
+    P.tta_on = (p->tta_scale != 0.0f && p->tta_scale != 1.0f) || p->tta_flip != 0;
+    if (P.tta_on && p->input_kind != YSB_INPUT_RAW_HEADS) return YSB_ERR_BAD_ARG;
+    P.tta_div = p->tta_scale == 0.0f ? 1.0f : p->tta_scale;
+    P.tta_flip = p->tta_flip;
+    P.tta_h = static_cast<float>(p->tta_img_h);
+    P.tta_w = static_cast<float>(p->tta_img_w);
 
     int64_t n = 0;
     for (int l = 0; l < L; ++l) {
@@ -272,7 +285,19 @@ int ysb_decode(const ysb_params *p, const void *const *d_heads, int num_heads, f
     Built b;
     const int st = build_plan(p, d_heads, num_heads, &b);
     if (st != YSB_OK) return st;
-    return cuda_status(launch_decode(b.plan, d_decoded, static_cast<cudaStream_t>(stream)));
+    return cuda_status(launch_decode(b.plan, d_decoded, b.plan.N, 0, static_cast<cudaStream_t>(stream)));
+}
+
+int ysb_decode_into(const ysb_params *p, const void *const *d_heads, int num_heads, float *d_decoded, int64_t rows_total,
+                    int64_t row_offset, void *stream)
+{
+    if (!d_heads || !d_decoded) return YSB_ERR_BAD_ARG;
+    if (p && p->input_kind != YSB_INPUT_RAW_HEADS) return YSB_ERR_BAD_ARG;
+    Built b;
+    const int st = build_plan(p, d_heads, num_heads, &b);
+    if (st != YSB_OK) return st;
+    if (row_offset < 0 || rows_total < row_offset + b.plan.N) return YSB_ERR_BAD_ARG;
+    return cuda_status(launch_decode(b.plan, d_decoded, rows_total, row_offset, static_cast<cudaStream_t>(stream)));
 }
 
 int ysb_filter_candidates(const ysb_params *p, const void *const *d_heads, int num_heads, uint64_t *d_keys,
@@ -283,7 +308,7 @@ int ysb_filter_candidates(const ysb_params *p, const void *const *d_heads, int n
     const int st = build_plan(p, d_heads, num_heads, &b);
     if (st != YSB_OK) return st;
     if (key_capacity < key_slots(b.plan)) return YSB_ERR_WORKSPACE;
-    return cuda_status(launch_filter(b.plan, b.vec, d_keys, key_capacity, d_counts, static_cast<cudaStream_t>(stream)));
+    return cuda_status(launch_filter(b.plan, b.vec, d_keys, key_capacity, d_counts, static_cast<cudaStream_t>(stream), true));
 }
 
 int ysb_select_nms(const ysb_params *p, const void *const *d_heads, int num_heads, const uint64_t *d_keys,
@@ -327,9 +352,91 @@ int ysb_postprocess(const ysb_params *p, const void *const *d_heads, int num_hea
     const int64_t slots = key_slots(b.plan);
     int32_t *d_counts = reinterpret_cast<int32_t *>(base + align256(sizeof(uint64_t) * static_cast<size_t>(slots) * b.plan.batch));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    st = cuda_status(launch_filter(b.plan, b.vec, d_keys, slots, d_counts, s));
+    st = cuda_status(launch_filter(b.plan, b.vec, d_keys, slots, d_counts, s, true));
     if (st != YSB_OK) return st;
     return cuda_status(launch_select_nms(b.plan, d_keys, slots, d_counts, d_dets, d_det_idx, d_det_cnt, s));
+}
+
+// ---- test-time augmentation: several passes, one merged candidate space -------------------------------------------
+struct BuiltPasses {
+    Built b[YSB_MAX_PASSES];
+    int64_t base[YSB_MAX_PASSES + 1];  // merged candidate index of candidate 0 of every pass; [n] = total
+    int64_t slots;                     // key slots per image over all passes
+};
+
+static int build_passes(const ysb_params *passes, int num_passes, const void *const *d_heads, const int32_t *heads_per_pass,
+                        BuiltPasses *out)
+{
+    if (!passes || !out || num_passes < 1 || num_passes > YSB_MAX_PASSES) return YSB_ERR_BAD_ARG;
+    if (d_heads && !heads_per_pass) return YSB_ERR_BAD_ARG;
+    int64_t base = 0, slots = 0;
+    int head0 = 0;
+    for (int i = 0; i < num_passes; ++i) {
+        const ysb_params *p = passes + i;
+        if (p->input_kind != YSB_INPUT_RAW_HEADS) return YSB_ERR_BAD_ARG;
+        // one evaluator, one hyp: everything but the geometry and the undo must agree with pass 0
+        const ysb_params *q = passes;
+        if (p->family != q->family || p->batch != q->batch || p->num_classes != q->num_classes ||
+            p->conf_thr != q->conf_thr || p->cls_thr != q->cls_thr || p->pre_nms_thr != q->pre_nms_thr ||
+            p->iou_thr != q->iou_thr || p->max_det != q->max_det || p->class_aware != q->class_aware ||
+            p->multi_label != q->multi_label || p->postprocess_bbox != q->postprocess_bbox ||
+            p->min_box_wh != q->min_box_wh || p->pre_nms_topk != q->pre_nms_topk ||
+            p->thresh_with_ctr != q->thresh_with_ctr)
+            return YSB_ERR_BAD_ARG;
+        const int nh = d_heads ? heads_per_pass[i] : 0;
+        const int st = build_plan(p, d_heads ? d_heads + head0 : nullptr, nh, &out->b[i]);
+        if (st != YSB_OK) return st;
+        head0 += nh;
+        out->base[i] = base;
+        out->b[i].plan.cand_base = static_cast<int>(base);
+        base += out->b[i].plan.N;
+        slots += key_slots(out->b[i].plan);
+        if (base > YSB_MAX_CANDIDATES) return YSB_ERR_LIMIT;
+    }
+    out->base[num_passes] = base;
+    out->slots = slots;
+    return YSB_OK;
+}
+
+int ysb_postprocess_tta_workspace_bytes(const ysb_params *passes, int num_passes, size_t *bytes_out)
+{
+    if (!bytes_out) return YSB_ERR_BAD_ARG;
+    BuiltPasses bp;
+    const int st = build_passes(passes, num_passes, nullptr, nullptr, &bp);
+    if (st != YSB_OK) return st;
+    const size_t batch = static_cast<size_t>(bp.b[0].plan.batch);
+    *bytes_out = align256(sizeof(uint64_t) * static_cast<size_t>(bp.slots) * batch) + align256(sizeof(int32_t) * 4 * batch) + 256;
+    return YSB_OK;
+}
+
+int ysb_postprocess_tta(const ysb_params *passes, int num_passes, const void *const *d_heads, const int32_t *heads_per_pass,
+                        void *d_workspace, size_t workspace_bytes, float *d_dets, int32_t *d_det_idx,
+                        int32_t *d_det_cnt, void *stream)
+{
+    if (!d_heads || !heads_per_pass || !d_workspace || !d_dets || !d_det_cnt) return YSB_ERR_BAD_ARG;
+    BuiltPasses bp;
+    int st = build_passes(passes, num_passes, d_heads, heads_per_pass, &bp);
+    if (st != YSB_OK) return st;
+    const size_t batch = static_cast<size_t>(bp.b[0].plan.batch);
+    const size_t need = align256(sizeof(uint64_t) * static_cast<size_t>(bp.slots) * batch) + align256(sizeof(int32_t) * 4 * batch) + 256;
+    if (workspace_bytes < need) return YSB_ERR_WORKSPACE;
+    uintptr_t base = (reinterpret_cast<uintptr_t>(d_workspace) + 255) & ~static_cast<uintptr_t>(255);
+    uint64_t *d_keys = reinterpret_cast<uint64_t *>(base);
+    int32_t *d_counts = reinterpret_cast<int32_t *>(base + align256(sizeof(uint64_t) * static_cast<size_t>(bp.slots) * batch));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // every pass appends its survivors to the same per-image key list (the counters are zeroed by the first pass only)
+    for (int i = 0; i < num_passes; ++i) {
+        st = cuda_status(launch_filter(bp.b[i].plan, bp.b[i].vec, d_keys, bp.slots, d_counts, s, i == 0));
+        if (st != YSB_OK) return st;
+    }
+    ExtraPasses X;
+    std::memset(&X, 0, sizeof(X));
+    X.n = num_passes - 1;
+    for (int i = 1; i < num_passes; ++i) {
+        X.base[i - 1] = static_cast<int>(bp.base[i]);
+        X.p[i - 1] = bp.b[i].plan;
+    }
+    return cuda_status(launch_select_nms_tta(bp.b[0].plan, X, d_keys, bp.slots, d_counts, d_dets, d_det_idx, d_det_cnt, s));
 }
 
 int ysb_nms_workspace_bytes(int64_t m, size_t *bytes_out)

@@ -49,7 +49,8 @@ __device__ __forceinline__ CandAddr cand_addr(const Plan &P, int img, int cand)
 // ROWS = candidates per CTA: 32 for channels-last heads (their rows are contiguous anyway), 128 for NCHW planes so that
 // every plane access of a CTA covers 512 contiguous bytes.
 template <int ROWS>
-__global__ void __launch_bounds__(kDecThreads) k_decode_rows(const __grid_constant__ Plan P, float *__restrict__ out)
+__global__ void __launch_bounds__(kDecThreads) k_decode_rows(const __grid_constant__ Plan P, float *__restrict__ out,
+                                                              int64_t rows_total, int64_t row_offset)
 {
     extern __shared__ __align__(16) float tile[];  // [ROWS][row_w]
     const int img = blockIdx.y;
@@ -88,14 +89,14 @@ __global__ void __launch_bounds__(kDecThreads) k_decode_rows(const __grid_consta
                 const float s0 = __shfl_sync(0xffffffffu, sv, qb), s1 = __shfl_sync(0xffffffffu, sv, qb + 1);
                 const float s2 = __shfl_sync(0xffffffffu, sv, qb + 2), s3 = __shfl_sync(0xffffffffu, sv, qb + 3);
                 if (side == 0 && r4 < nrows) {
-                    const float4 b = v8_box_from_sides(P, c0 + r4, s0, s1, s2, s3);
+                    const float4 b = tta_undo(P, v8_box_from_sides(P, c0 + r4, s0, s1, s2, s3));
                     float *t = tile + r4 * rw + P.box_col;
                     t[0] = b.x; t[1] = b.y; t[2] = b.z; t[3] = b.w;
                 }
             }
         } else if (threadIdx.x >= kDecThreads - ROWS && threadIdx.x - (kDecThreads - ROWS) < nrows) {
             const int rb = threadIdx.x - (kDecThreads - ROWS);
-            const float4 b = decode_box_cols(P, img, c0 + rb);
+            const float4 b = tta_undo(P, decode_box_cols(P, img, c0 + rb));
             float *t = tile + rb * rw + P.box_col;
             t[0] = b.x; t[1] = b.y; t[2] = b.z; t[3] = b.w;
         }
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(kDecThreads) k_decode_rows(const __grid_consta
         }
         if (warp == 0 && lane < nrows) {
             const int cand = c0 + lane;
-            const float4 b = decode_box_cols(P, img, cand);
+            const float4 b = tta_undo(P, decode_box_cols(P, img, cand));
             float *t = tile + lane * rw + P.box_col;
             t[0] = b.x; t[1] = b.y; t[2] = b.z; t[3] = b.w;
             if (P.obj_col >= 0) {
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(kDecThreads) k_decode_rows(const __grid_consta
         }
     }
     __syncthreads();
-    float *dst = out + (static_cast<size_t>(img) * P.N + c0) * rw;
+    float *dst = out + (static_cast<size_t>(img) * rows_total + row_offset + c0) * rw;
     const int nfl = nrows * rw;
     if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(tile)) & 15u) == 0) {
         const int nv = nfl >> 2;
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(kDecThreads) k_decode_rows(const __grid_consta
 }
 
 template <int ROWS>
-static cudaError_t launch_decode_t(const Plan &P, float *d_out, cudaStream_t stream)
+static cudaError_t launch_decode_t(const Plan &P, float *d_out, int64_t rows_total, int64_t row_offset, cudaStream_t stream)
 {
     const size_t smem = static_cast<size_t>(ROWS) * P.row_w * sizeof(float);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
@@ -150,16 +151,17 @@ static cudaError_t launch_decode_t(const Plan &P, float *d_out, cudaStream_t str
         if (e != cudaSuccess) return e;
     }
     const dim3 grid((P.N + ROWS - 1) / ROWS, P.batch);
-    k_decode_rows<ROWS><<<grid, kDecThreads, smem, stream>>>(P, d_out);
+    k_decode_rows<ROWS><<<grid, kDecThreads, smem, stream>>>(P, d_out, rows_total, row_offset);
     return cudaGetLastError();
 }
 
-cudaError_t launch_decode(const Plan &P, float *d_out, cudaStream_t stream)
+// rows_total / row_offset: the pass fills rows [row_offset, row_offset + N) of a (batch, rows_total, C') tensor
+cudaError_t launch_decode(const Plan &P, float *d_out, int64_t rows_total, int64_t row_offset, cudaStream_t stream)
 {
     if (P.batch == 0 || P.N == 0) return cudaSuccess;
     if (P.layout == LAYOUT_PLANES && static_cast<size_t>(128) * P.row_w * sizeof(float) <= 100 * 1024)
-        return launch_decode_t<128>(P, d_out, stream);
-    return launch_decode_t<32>(P, d_out, stream);
+        return launch_decode_t<128>(P, d_out, rows_total, row_offset, stream);
+    return launch_decode_t<32>(P, d_out, rows_total, row_offset, stream);
 }
 
 }  // namespace ysb

@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_filter_planes(const __grid_co
                 score, c, pre);
             npre += pre ? 1 : 0;
             if (ok) {
-                out[j] = pack_key(score, static_cast<uint32_t>(cand0 + j), static_cast<uint32_t>(c));
+                out[j] = pack_key(score, static_cast<uint32_t>(P.cand_base + cand0 + j), static_cast<uint32_t>(c));
                 okm |= 1u << j;
                 const uint32_t sb = __float_as_uint(score);
                 smax_bits = max(smax_bits, sb);
@@ -459,7 +459,7 @@ k_filter_planes_bulk(const __grid_constant__ Plan P, const __grid_constant__ Bul
                         P, m1[i], m2[i], k0[i], objv[i], [&](int kk) { return __ldg(cj + static_cast<size_t>(kk) * hw); }, score, cid, pre);
                     npre += pre ? 1 : 0;
                     if (ok) {
-                        out[i] = pack_key(score, static_cast<uint32_t>(lv.cand_off + w.a * lv.hw + w.pos0 + 4 * t + i), static_cast<uint32_t>(cid));
+                        out[i] = pack_key(score, static_cast<uint32_t>(P.cand_base + lv.cand_off + w.a * lv.hw + w.pos0 + 4 * t + i), static_cast<uint32_t>(cid));
                         okm |= 1u << i;
                         const uint32_t sb = __float_as_uint(score);
                         smax_bits = max(smax_bits, sb);
@@ -682,7 +682,7 @@ k_filter_planes_async(const __grid_constant__ Plan P, int64_t total_units, uint6
                     P, m1[i], m2[i], k0[i], objv[i], [&](int kk) { return __ldg(cj + static_cast<size_t>(kk) * hw); }, score, cid, pre);
                 npre += pre ? 1 : 0;
                 if (ok) {
-                    out[i] = pack_key(score, static_cast<uint32_t>(r.cand0 + i), static_cast<uint32_t>(cid));
+                    out[i] = pack_key(score, static_cast<uint32_t>(P.cand_base + r.cand0 + i), static_cast<uint32_t>(cid));
                     okm |= 1u << i;
                     const uint32_t sb = __float_as_uint(score);
                     smax_bits = max(smax_bits, sb);
@@ -800,7 +800,7 @@ __global__ void __launch_bounds__(kRowsTile) k_filter_rows(const __grid_constant
             ok = decide_candidate<false>(P, m1, m2, k0, objv, [&](int kk) { return cls[kk]; }, score, c, pre);
         npre = pre ? 1 : 0;
         if (ok) {
-            out[0] = pack_key(score, static_cast<uint32_t>(cand), static_cast<uint32_t>(c));
+            out[0] = pack_key(score, static_cast<uint32_t>(P.cand_base + cand), static_cast<uint32_t>(c));
             okm = 1u;
             smax_bits = __float_as_uint(score);
             smin_inv = ~smax_bits;
@@ -909,7 +909,7 @@ __global__ void __launch_bounds__(256) k_filter_multilabel(const __grid_constant
             float sk;
             const float p = score_of(k, sk);
             if (passes(p)) {
-                if (at < key_cap) dst[at] = pack_key(p, static_cast<uint32_t>(cand), static_cast<uint32_t>(k));
+                if (at < key_cap) dst[at] = pack_key(p, static_cast<uint32_t>(P.cand_base + cand), static_cast<uint32_t>(k));
                 ++at;
             }
         }
@@ -930,10 +930,12 @@ static int g_bulk_ppt = [] {
     return v ? atoi(v) : 0;
 }();
 
+// zero_counts = false: append to the key lists / counters a previous pass left (test-time-augmentation passes)
 cudaError_t launch_filter(const Plan &P, int vec, uint64_t *d_keys, int64_t key_cap, int32_t *d_counts,
-                          cudaStream_t stream)
+                          cudaStream_t stream, bool zero_counts)
 {
-    cudaError_t e = cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * 4 * static_cast<size_t>(P.batch), stream);
+    cudaError_t e = cudaSuccess;
+    if (zero_counts) e = cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * 4 * static_cast<size_t>(P.batch), stream);
     if (e != cudaSuccess) return e;
     if (P.batch == 0 || P.N == 0) return cudaSuccess;
     if (P.multi_label) {

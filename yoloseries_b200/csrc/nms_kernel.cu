@@ -226,11 +226,26 @@ __device__ void bitonic_sort_desc(uint64_t *keys, int n)
     __syncthreads();
 }
 
-template <bool ARRAY>
+// Plan a merged candidate index belongs to (test-time-augmentation passes); cand becomes the index inside that pass.
+__device__ __forceinline__ const Plan &pass_of(const Plan &P, const NoExtraPasses &, int &) { return P; }
+__device__ __forceinline__ const Plan &pass_of(const Plan &P, const ExtraPasses &X, int &cand)
+{
+    int sel = -1;
+#pragma unroll
+    for (int i = 0; i < YSB_MAX_PASSES - 1; ++i)
+        if (i < X.n && cand >= X.base[i]) sel = i;
+    if (sel < 0) return P;
+    cand -= X.base[sel];
+    return X.p[sel];
+}
+
+// EXTRA = NoExtraPasses (one set of heads) or ExtraPasses (TTA: boxes are decoded from the pass a candidate came from;
+// thresholds / NMS settings are those of P, identical in every pass).
+template <bool ARRAY, typename EXTRA>
 __global__ void __launch_bounds__(kThreads, 1)
-k_select_nms(const __grid_constant__ Plan P, const uint64_t *__restrict__ keys_all, int64_t key_cap,
-             const int32_t *__restrict__ counts, float *__restrict__ dets, int32_t *__restrict__ det_idx,
-             int32_t *__restrict__ det_cnt, const ArrayArgs aa)
+k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, const uint64_t *__restrict__ keys_all,
+             int64_t key_cap, const int32_t *__restrict__ counts, float *__restrict__ dets,
+             int32_t *__restrict__ det_idx, int32_t *__restrict__ det_cnt, const ArrayArgs aa)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmsSmem &S = *reinterpret_cast<NmsSmem *>(smem_raw);
@@ -315,18 +330,28 @@ k_select_nms(const __grid_constant__ Plan P, const uint64_t *__restrict__ keys_a
                     int cand = 0;
                     if (i < n_use) {
                         cand = static_cast<int>(key_cand(S.keys[i]));
-                        sv = v8_side_value(P, img, cand, side);
+                        const Plan &Q = pass_of(P, X, cand);
+                        sv = v8_side_value(Q, img, cand, side);
                     }
                     const unsigned qb = (tid & 31) & ~3u;
                     const float s0 = __shfl_sync(0xffffffffu, sv, qb), s1 = __shfl_sync(0xffffffffu, sv, qb + 1);
                     const float s2 = __shfl_sync(0xffffffffu, sv, qb + 2), s3 = __shfl_sync(0xffffffffu, sv, qb + 3);
-                    if (side == 0 && i < n_use) S.raw[i] = v8_box_from_sides(P, cand, s0, s1, s2, s3);
+                    if (side == 0 && i < n_use) {
+                        int full = static_cast<int>(key_cand(S.keys[i]));
+                        const Plan &Q = pass_of(P, X, full);
+                        S.raw[i] = tta_undo(Q, v8_box_from_sides(Q, full, s0, s1, s2, s3));
+                    }
                     decoded_upto = min(n_use, decoded_upto + kThreads / 4);
                 } else {
                     const int i = decoded_upto + tid;
                     if (i < n_use) {
-                        const int cand = static_cast<int>(key_cand(S.keys[i]));
-                        S.raw[i] = ARRAY ? __ldg(aa.boxes + cand) : candidate_xyxy(P, img, cand);
+                        int cand = static_cast<int>(key_cand(S.keys[i]));
+                        if (ARRAY) {
+                            S.raw[i] = __ldg(aa.boxes + cand);
+                        } else {
+                            const Plan &Q = pass_of(P, X, cand);
+                            S.raw[i] = candidate_xyxy(Q, img, cand);
+                        }
                     }
                     decoded_upto = min(n_use, decoded_upto + kThreads);
                 }
@@ -436,8 +461,11 @@ k_select_nms(const __grid_constant__ Plan P, const uint64_t *__restrict__ keys_a
             K2_ACC(12);
         }
         if (window) {  // the count filter below needs every survivor's box (single tranche holds them all)
-            for (int i = decoded_upto + tid; i < n_use; i += kThreads)
-                S.raw[i] = candidate_xyxy(P, img, static_cast<int>(key_cand(S.keys[i])));
+            for (int i = decoded_upto + tid; i < n_use; i += kThreads) {
+                int cand = static_cast<int>(key_cand(S.keys[i]));
+                const Plan &Q = pass_of(P, X, cand);
+                S.raw[i] = candidate_xyxy(Q, img, cand);
+            }
             __syncthreads();
         }
         K2_STAMP(4);
@@ -562,12 +590,27 @@ cudaError_t launch_select_nms(const Plan &P, const uint64_t *d_keys, int64_t key
     if (P.batch == 0) return cudaSuccess;
     // per-device attribute; set on every launch (host-side, sub-microsecond) so that a process driving several
     // devices never launches with the default 48 KB limit
-    cudaError_t e = cudaFuncSetAttribute(k_select_nms<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k_select_nms<false, NoExtraPasses>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(sizeof(NmsSmem)));
     if (e != cudaSuccess) return e;
     ArrayArgs aa{};
-    k_select_nms<false><<<P.batch, kThreads, sizeof(NmsSmem), stream>>>(P, d_keys, key_cap, d_counts, d_dets, d_det_idx,
-                                                                         d_det_cnt, aa);
+    k_select_nms<false, NoExtraPasses><<<P.batch, kThreads, sizeof(NmsSmem), stream>>>(
+        P, NoExtraPasses{}, d_keys, key_cap, d_counts, d_dets, d_det_idx, d_det_cnt, aa);
+    return cudaGetLastError();
+}
+
+// test-time augmentation: one selection/NMS over the key lists the passes appended to; X describes passes 1..n
+cudaError_t launch_select_nms_tta(const Plan &P, const ExtraPasses &X, const uint64_t *d_keys, int64_t key_cap,
+                                  const int32_t *d_counts, float *d_dets, int32_t *d_det_idx, int32_t *d_det_cnt,
+                                  cudaStream_t stream)
+{
+    if (P.batch == 0) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(k_select_nms<false, ExtraPasses>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(sizeof(NmsSmem)));
+    if (e != cudaSuccess) return e;
+    ArrayArgs aa{};
+    k_select_nms<false, ExtraPasses><<<P.batch, kThreads, sizeof(NmsSmem), stream>>>(P, X, d_keys, key_cap, d_counts, d_dets,
+                                                                                      d_det_idx, d_det_cnt, aa);
     return cudaGetLastError();
 }
 
@@ -615,7 +658,8 @@ cudaError_t launch_array_nms(const float *d_boxes, const float *d_scores, int64_
     cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int32_t) * 4, stream);
     if (e != cudaSuccess) return e;
     k_array_keys<<<static_cast<unsigned>((m + 255) / 256), 256, 0, stream>>>(d_scores, static_cast<int>(m), keys, counts);
-    e = cudaFuncSetAttribute(k_select_nms<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(NmsSmem)));
+    e = cudaFuncSetAttribute(k_select_nms<true, NoExtraPasses>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(sizeof(NmsSmem)));
     if (e != cudaSuccess) return e;
     Plan P;
     memset(&P, 0, sizeof(P));
@@ -631,7 +675,8 @@ cudaError_t launch_array_nms(const float *d_boxes, const float *d_scores, int64_
     aa.iou_kind = iou_kind;
     aa.cmp = cmp;
     aa.thr32 = static_cast<float>(iou_thr);
-    k_select_nms<true><<<1, kThreads, sizeof(NmsSmem), stream>>>(P, keys, m, counts, nullptr, nullptr, nullptr, aa);
+    k_select_nms<true, NoExtraPasses><<<1, kThreads, sizeof(NmsSmem), stream>>>(P, NoExtraPasses{}, keys, m, counts, nullptr,
+                                                                                 nullptr, nullptr, aa);
     return cudaGetLastError();
 }
 

@@ -63,8 +63,12 @@ def _level_shapes(family, flat, num_class):
 
 
 def make_params(family, hyp, batch, img_h, img_w, level_shapes=None, anchors=None, input_kind=_lib.INPUT_RAW_HEADS,
-                compute_metric=False, num_anchors=None, decoded_rows=0):
-    """Build ``ysb_params`` from the reference's flat ``hyp`` dict (SURVEY.md section 5 lists the keys)."""
+                compute_metric=False, num_anchors=None, decoded_rows=0, tta=None):
+    """Build ``ysb_params`` from the reference's flat ``hyp`` dict (SURVEY.md section 5 lists the keys).
+
+    ``tta`` = (scale, flip_axis, org_h, org_w) describes one test-time-augmentation pass (trainer/eval_yolov5.py:152-179):
+    the boxes decoded from this pass's heads are divided by ``scale`` and un-flipped (axis 2 or 3) against the size of
+    the un-augmented input."""
     p = YsbParams()
     p.family = _lib.FAMILY_IDS[family]
     p.input_kind = input_kind
@@ -85,6 +89,10 @@ def make_params(family, hyp, batch, img_h, img_w, level_shapes=None, anchors=Non
     p.thresh_with_ctr = int(bool(hyp.get("thresh_with_ctr", True)))
     p.dfl_bins = int(hyp.get("reg", 16))
     p.decoded_rows = int(decoded_rows)
+    if tta is not None:
+        p.tta_scale = float(tta[0])
+        p.tta_flip = int(tta[1] or 0)
+        p.tta_img_h, p.tta_img_w = int(tta[2]), int(tta[3])
     scale = hyp.get("tar_box_scale_factor", [0.1, 0.1, 0.2, 0.2])
     for i in range(4):
         p.reg_scale[i] = float(scale[i])
@@ -186,7 +194,7 @@ class PostProcessor:
         self._cache = {}
 
     # ---- plumbing ------------------------------------------------------------------------------------------
-    def _prepare(self, flat, batch, img_h, img_w, input_kind):
+    def _prepare(self, flat, batch, img_h, img_w, input_kind, tta=None):
         dev = flat[0].device
         if dev.type != "cuda":
             raise RuntimeError("yoloseries_b200 runs on CUDA devices only (no CPU fallback); got " + str(dev))
@@ -201,11 +209,11 @@ class PostProcessor:
             shapes = [(img_h // s, img_w // s) for s in strides]
         na = flat[0].shape[1] if (self.family == "yolox" and input_kind == _lib.INPUT_RAW_HEADS) else None
         rows = int(flat[0].shape[1]) if input_kind == _lib.INPUT_DECODED_ROWS else 0
-        key = (batch, img_h, img_w, input_kind, tuple(shapes or ()), dev.index, na, rows)
+        key = (batch, img_h, img_w, input_kind, tuple(shapes or ()), dev.index, na, rows, tta)
         ent = self._cache.get(key)
         if ent is None:
             params = make_params(self.family, self.hyp, batch, img_h, img_w, shapes, self.anchors, input_kind,
-                                 self.compute_metric, na, rows)
+                                 self.compute_metric, na, rows, tta)
             n = ctypes.c_int64()
             rw = ctypes.c_int32()
             _lib.check(self._lib.ysb_num_candidates(ctypes.byref(params), ctypes.byref(n), ctypes.byref(rw)),
@@ -251,6 +259,61 @@ class PostProcessor:
         _lib.check(self._lib.ysb_postprocess(ctypes.byref(ent["params"]), ptrs, len(flat), ws.data_ptr(), ws.numel(),
                                              out.dets.data_ptr(), out.det_idx.data_ptr(), out.det_cnt.data_ptr(),
                                              self._stream()), "ysb_postprocess")
+        return out
+
+    # ---- test-time augmentation (trainer/eval_yolov5.py:152-179 and the same method of every evaluator) ------------
+    def _tta_entries(self, passes, org_hw):
+        """passes: [(heads, img_h, img_w, scale, flip_axis), ...] -> [(flat heads, cache entry), ...]."""
+        if not 1 <= len(passes) <= _lib.YSB_MAX_PASSES:
+            raise ValueError(f"1..{_lib.YSB_MAX_PASSES} passes, got {len(passes)}")
+        ents = []
+        for heads, img_h, img_w, scale, flip in passes:
+            flat = flatten_heads(self.family, heads)
+            tta = (float(scale), int(flip or 0), int(org_hw[0]), int(org_hw[1]))
+            ents.append((flat, self._prepare(flat, flat[0].shape[0], int(img_h), int(img_w), _lib.INPUT_RAW_HEADS, tta)))
+        if len({e["params"].batch for _, e in ents}) != 1:
+            raise ValueError("every pass must hold the same images")
+        return ents
+
+    def decode_tta(self, passes, org_hw):
+        """test_time_augmentation: every pass decoded, un-scaled and un-flipped straight into its slot of the merged
+        (b, sum N_i, C') tensor.  Returns (merged, [per-pass views])."""
+        ents = self._tta_entries(passes, org_hw)
+        batch, total = ents[0][1]["params"].batch, sum(e["N"] for _, e in ents)
+        out = torch.empty((batch, total, ents[0][1]["row_w"]), dtype=torch.float32, device=ents[0][0][0].device)
+        off, views = 0, []
+        for flat, ent in ents:
+            _lib.check(self._lib.ysb_decode_into(ctypes.byref(ent["params"]), _lib.head_pointer_array(flat), len(flat),
+                                                 out.data_ptr(), total, off, self._stream()), "ysb_decode_into")
+            views.append(out[:, off:off + ent["N"]])
+            off += ent["N"]
+        return out, views
+
+    def run_tta(self, passes, org_hw):
+        """The whole path over several augmented passes without the merged tensor (ysb_postprocess_tta).  Candidate
+        indices (det_idx) count through the passes in order, like rows of the reference's concatenated tensor."""
+        ents = self._tta_entries(passes, org_hw)
+        dev = ents[0][0][0].device
+        batch = ents[0][1]["params"].batch
+        if batch == 0:
+            return DetectionBuffers(0, int(self.hyp["max_predictions_per_img"]), dev)
+        n = len(ents)
+        key = ("tta", dev.index) + tuple(id(e) for _, e in ents)
+        bundle = self._cache.get(key)
+        if bundle is None:
+            arr = (YsbParams * n)(*[e["params"] for _, e in ents])
+            ws = ctypes.c_size_t()
+            _lib.check(self._lib.ysb_postprocess_tta_workspace_bytes(arr, n, ctypes.byref(ws)),
+                       "ysb_postprocess_tta_workspace_bytes")
+            bundle = dict(params=arr, workspace=torch.empty(max(ws.value, 1), dtype=torch.uint8, device=dev),
+                          out=DetectionBuffers(batch, arr[0].max_det, dev), keep=[e for _, e in ents])
+            self._cache[key] = bundle
+        flat_all = [t for flat, _ in ents for t in flat]
+        per_pass = (ctypes.c_int32 * n)(*[len(flat) for flat, _ in ents])
+        out, ws = bundle["out"], bundle["workspace"]
+        _lib.check(self._lib.ysb_postprocess_tta(bundle["params"], n, _lib.head_pointer_array(flat_all), per_pass,
+                                                 ws.data_ptr(), ws.numel(), out.dets.data_ptr(), out.det_idx.data_ptr(),
+                                                 out.det_cnt.data_ptr(), self._stream()), "ysb_postprocess_tta")
         return out
 
     def capture(self, heads, img_h, img_w, decoded=False):

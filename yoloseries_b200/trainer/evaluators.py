@@ -45,11 +45,11 @@ class _Evaluator:
     @torch.no_grad()
     def __call__(self, inputs):
         if self.use_tta:
-            merged, independent = self.test_time_augmentation(inputs)
             if self.hyp.get("wfb", False):
                 raise NotImplementedError("weighted-box-fusion (hyp['wfb']) is a 'next' row (SURVEY.md 8f rank 3)")
-            outs = self.numba_nms(merged)
-            return [torch.from_numpy(x) if x is not None else None for x in outs]
+            # three model forwards, then ONE fused call: no decoded or merged tensor is written (ysb_postprocess_tta)
+            out = self._pp.run_tta(self._tta_passes(inputs), (inputs.size(2), inputs.size(3)))
+            return self._pp.to_list(out)
         heads = self._model(inputs)
         out = self._pp.run(heads, inputs.size(2), inputs.size(3))
         return self._pp.to_list(out)
@@ -77,30 +77,24 @@ class _Evaluator:
         with the live path's semantics, returning tensors."""
         return [torch.from_numpy(x) if x is not None else None for x in self.numba_nms(preds_out)]
 
-    # ---- TTA (SURVEY.md 8f rank 2): the reference's own torch expressions, kept on the device ----------------------
-    def test_time_augmentation(self, inputs):
-        img_h, img_w = inputs.size(2), inputs.size(3)
-        b0 = self._pp_box_col()
-        preds_all = []
+    # ---- TTA (SURVEY.md 8f rank 2) -------------------------------------------------------------------------------
+    def _tta_passes(self, inputs):
+        """The three augmented forwards of test_time_augmentation (trainer/eval_yolov5.py:158-168): scale 1 / 0.83 / 0.67,
+        flip none / along h / along w.  Returns [(raw heads, pass_h, pass_w, scale, flip_axis), ...]."""
+        passes = []
         for s, f in zip([1, 0.83, 0.67], [None, 2, 3]):
             img = inputs.flip(dims=(f,)) if f else inputs
             img = self.scale_img(img, s)
-            p = self.do_inference(img)
-            p[..., b0:b0 + 4] /= s
-            if self._box_cols_xywh:
-                if f == 2:
-                    p[..., b0 + 1] = img_h - p[..., b0 + 1]
-                if f == 3:
-                    p[..., b0 + 0] = img_w - p[..., b0 + 0]
-            else:
-                if f == 2:
-                    ymin, ymax = img_h - p[..., b0 + 3], img_h - p[..., b0 + 1]
-                    p[..., b0 + 1], p[..., b0 + 3] = ymin, ymax
-                if f == 3:
-                    xmin, xmax = img_w - p[..., b0 + 2], img_w - p[..., b0 + 0]
-                    p[..., b0 + 0], p[..., b0 + 2] = xmin, xmax
-            preds_all.append(p)
-        return torch.cat(preds_all, dim=1).contiguous(), preds_all
+            passes.append((self._model(img), img.size(2), img.size(3), s, f))
+        return passes
+
+    def test_time_augmentation(self, inputs):
+        """trainer/eval_yolov5.py:152-179 (xywh rows; xyxy rows: eval_yolov8.py:40-73, eval_retinanet.py:148-182,
+        eval_fcos.py:90-123) -> (merged (b, sum N_i, C'), [per-pass tensors]).  Each pass is decoded, divided by its
+        scale and un-flipped by one ysb_decode_into launch writing straight into its slot of the merged tensor; the
+        per-pass tensors are views of it."""
+        merged, views = self._pp.decode_tta(self._tta_passes(inputs), (inputs.size(2), inputs.size(3)))
+        return merged, views
 
     def _pp_box_col(self):
         return self.num_class if self.family.startswith("retinanet") else 0
