@@ -266,3 +266,39 @@ def test_cuda_graph_capture_replays_with_refilled_heads():
             assert (g is None) == (w is None)
             if g is not None:
                 np.testing.assert_array_equal(g, w)
+
+
+def test_filter_kernel_variants_emit_the_same_survivors():
+    """The profiling variants of the filter kernel (cp.async ring, 1-D bulk-copy TMA ring, 2-D tensor-map TMA ring) are
+    selected by an environment variable read at library load: run each in a subprocess and compare survivor sets."""
+    import os
+    import subprocess
+    import sys
+    child = r'''
+import hashlib, sys, torch
+sys.path.insert(0, ".")
+import oracle
+from yoloseries_b200 import synth
+from yoloseries_b200.engine import PostProcessor
+for fam, img in (("yolov5", 320), ("yolox", 256), ("yolov8", 128)):
+    pp = PostProcessor(fam, oracle.default_hyp(num_class=80),
+                       anchors=torch.tensor(synth.V5_ANCHORS_PX) if fam == "yolov5" else None)
+    heads = synth.make_heads(fam, 3, img, img, 80, "dense", seed=9, device="cuda")
+    keys, counts = pp.filter_only(heads, img, img)
+    torch.cuda.synchronize()
+    h = hashlib.sha1(counts.cpu().numpy().tobytes())
+    for i in range(3):
+        h.update(torch.sort(keys[i, : int(counts[i, 0])]).values.cpu().numpy().tobytes())
+    print(fam, int(counts[:, 0].sum()), h.hexdigest())
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for variant, ppt in (("1", "0"), ("3", "8"), ("3", "43"), ("2", "4"), ("0", "0")):
+        env = dict(os.environ, YSB_FILTER_VARIANT=variant, YSB_BULK_PPT=ppt)
+        r = subprocess.run([sys.executable, "-c", child], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-1500:]
+        outs[(variant, ppt)] = r.stdout.strip().splitlines()[-3:]
+    base = outs[("1", "0")]
+    assert len(base) == 3 and all(int(line.split()[1]) > 0 for line in base)
+    for k, v in outs.items():
+        assert v == base, (k, v, base)

@@ -13,7 +13,10 @@
 //
 // Output: one 64-bit sort key per survivor, written with warp-aggregated atomics (order inside an image is
 // irrelevant: the key carries the candidate index, see pack_key).
+#include <cuda.h>
+
 #include <cstdlib>
+#include <cstring>
 
 #include "ysb_internal.cuh"
 
@@ -325,8 +328,8 @@ struct BulkItem {
     int img, l, a, pos0, npos;
 };
 
-template <int kItemPos>
-__device__ __forceinline__ BulkItem bulk_item(const Plan &P, const BulkCfg &cfg, int it)
+template <int kItemPos, typename CFG>
+__device__ __forceinline__ BulkItem bulk_item(const Plan &P, const CFG &cfg, int it)
 {
     BulkItem w;
     w.img = it / cfg.items_per_img;
@@ -501,6 +504,238 @@ static cudaError_t launch_bulk(const Plan &P, int num_sms, uint64_t *d_keys, int
     }
     const int grid = total < num_sms ? total : num_sms;
     k_filter_planes_bulk<CW, PL><<<grid, kBulkThreads, smem, stream>>>(P, cfg, total, d_keys, key_cap, d_counts);
+    return cudaGetLastError();
+}
+
+// -------------------------------------------------------------------------------------------------------
+// planes layout, 2-D tensor-map TMA version (cp.async.bulk.tensor.2d, SASS UTMALDG).
+//
+// Each level's head tensor is described to the TMA unit as a 2-D array [rows = batch*A*channels][hw positions]; ONE
+// request moves a box of PL consecutive channel rows x up to 256 positions into shared memory, so a ring stage
+// (PL planes x 128*CW positions) costs CW/2 requests instead of PL*... per-row bulk copies (the 1-D ring above was
+// bound by the producer's request rate).  Out-of-range positions of the last block of a plane are zero-filled by the
+// TMA unit without DRAM traffic.  Streamed rows of an (image, anchor): [objectness,] class 0 .. C-1 -- contiguous
+// channels for YOLOv5 / YOLOX (objectness is the channel before class 0) and for objectness-free heads (YOLOv8).
+// -------------------------------------------------------------------------------------------------------
+struct TmaMaps {
+    CUtensorMap m[YSB_MAX_LEVELS];
+};
+struct TmaCfg {
+    int stages;
+    int nq;          // streamed rows per (image, anchor)
+    int obj_first;   // row 0 is the objectness plane
+    int row0;        // channel of the first streamed row inside an (image, anchor) block
+    int items_per_img;
+    int item_off[YSB_MAX_LEVELS];
+    int blocks_per_anchor[YSB_MAX_LEVELS];
+    int box0[YSB_MAX_LEVELS];  // positions per request on this level: min(256, hw)
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap *map, int c0, int c1, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+                 : "memory");
+}
+
+template <int CW, int PL, int BPS>
+__global__ void __launch_bounds__((CW + 1) * 32, BPS)
+k_filter_planes_tma(const __grid_constant__ Plan P, const __grid_constant__ TmaCfg cfg, const __grid_constant__ TmaMaps maps,
+                    int total_items, uint64_t *__restrict__ keys, int64_t key_cap, int32_t *__restrict__ counts)
+{
+    constexpr int kItemPos = 128 * CW;
+    constexpr uint32_t kStageBytes = PL * kItemPos * 4;
+    extern __shared__ __align__(128) unsigned char bulk_smem[];
+    const uint32_t ring = (smem_u32(bulk_smem) + 127u) & ~127u;
+    const uint32_t full0 = ring + static_cast<uint32_t>(cfg.stages) * kStageBytes;
+    const uint32_t empty0 = full0 + 8u * cfg.stages;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < cfg.stages; ++s) {
+            mbar_init(full0 + 8u * s, 1);
+            mbar_init(empty0 + 8u * s, CW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int nchunks = (cfg.nq + PL - 1) / PL;
+    int stage = 0;
+    uint32_t phase = 0;
+    // items are numbered image-fastest: concurrently running CTAs append to different per-image counters
+    if (warp == CW) {
+        // ===== producer warp: lane r issues request r (256 positions x PL rows) of the stage =====
+        for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+            const int img = it % P.batch;
+            BulkItem w = bulk_item<kItemPos>(P, cfg, it / P.batch);
+            const int box0 = cfg.box0[w.l];
+            const int nreq = (w.npos + box0 - 1) / box0;
+            const int row_base = (img * P.A + w.a) * P.cls_nch + cfg.row0;
+            const uint32_t req_bytes = static_cast<uint32_t>(PL * box0) * 4u;
+            for (int c = 0; c < nchunks; ++c) {
+                mbar_wait(empty0 + 8u * stage, phase ^ 1u);
+                if (lane == 0) mbar_expect_tx(full0 + 8u * stage, req_bytes * nreq);
+                __syncwarp();
+                if (lane < nreq)
+                    tma_load_2d(ring + stage * kStageBytes + lane * req_bytes, &maps.m[w.l], w.pos0 + lane * box0,
+                                row_base + c * PL, full0 + 8u * stage);
+                if (++stage == cfg.stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else {
+        // ===== consumer warps: thread t owns positions pos0 + 4t .. 4t+3 =====
+        const int t = threadIdx.x;
+        const int nobj = cfg.obj_first;
+        for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+            const int img = it % P.batch;
+            BulkItem w = bulk_item<kItemPos>(P, cfg, it / P.batch);
+            w.img = img;
+            const bool active = 4 * t < w.npos;  // H*W % 4 == 0: a thread's four positions are all valid or all not
+            const int box0 = cfg.box0[w.l];
+            const int req = (4 * t) / box0;
+            const uint32_t row_pitch = static_cast<uint32_t>(box0) * 4u;
+            const uint32_t my_off = static_cast<uint32_t>(req) * (PL * row_pitch) + static_cast<uint32_t>(4 * t - req * box0) * 4u;
+            float m1[4], m2[4], objv[4];
+            int k0[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { m1[i] = -INFINITY; m2[i] = -INFINITY; objv[i] = 0.0f; k0[i] = 0; }
+            for (int c = 0; c < nchunks; ++c) {
+                mbar_wait(full0 + 8u * stage, phase);
+                const uint32_t src = ring + stage * kStageBytes + my_off;
+                if (active) {
+                    const int q0 = c * PL;
+                    if (q0 >= nobj && q0 + PL <= cfg.nq) {
+#pragma unroll
+                        for (int j = 0; j < PL; ++j) {
+                            const float4 v = lds128(src + j * row_pitch);
+                            const int k = q0 - nobj + j;
+                            top2_update(v.x, k, m1[0], m2[0], k0[0]);
+                            top2_update(v.y, k, m1[1], m2[1], k0[1]);
+                            top2_update(v.z, k, m1[2], m2[2], k0[2]);
+                            top2_update(v.w, k, m1[3], m2[3], k0[3]);
+                        }
+                    } else {
+                        const int nq = min(PL, cfg.nq - q0);
+#pragma unroll
+                        for (int j = 0; j < PL; ++j) {
+                            if (j < nq) {
+                                const float4 v = lds128(src + j * row_pitch);
+                                const int q = q0 + j;
+                                if (q < nobj) {
+                                    objv[0] = v.x; objv[1] = v.y; objv[2] = v.z; objv[3] = v.w;
+                                } else {
+                                    const int k = q - nobj;
+                                    top2_update(v.x, k, m1[0], m2[0], k0[0]);
+                                    top2_update(v.y, k, m1[1], m2[1], k0[1]);
+                                    top2_update(v.z, k, m1[2], m2[2], k0[2]);
+                                    top2_update(v.w, k, m1[3], m2[3], k0[3]);
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty0 + 8u * stage);
+                if (++stage == cfg.stages) { stage = 0; phase ^= 1u; }
+            }
+            const LevelDesc &lv = P.lv[w.l];
+            const size_t hw = static_cast<size_t>(lv.hw);
+            const float *cbase = lv.p0 + (static_cast<size_t>(w.img * P.A + w.a) * P.cls_nch + P.cls_ch) * hw + w.pos0 + 4 * t;
+            uint64_t out[4];
+            unsigned okm = 0u;
+            int npre = 0;
+            uint32_t smax_bits = 0u, smin_inv = 0u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                out[i] = 0ull;
+                if (active) {
+                    const float *cj = cbase + i;
+                    float score;
+                    int cid;
+                    bool pre;
+                    const bool ok = decide_candidate<false>(
+                        P, m1[i], m2[i], k0[i], objv[i], [&](int kk) { return __ldg(cj + static_cast<size_t>(kk) * hw); }, score, cid, pre);
+                    npre += pre ? 1 : 0;
+                    if (ok) {
+                        out[i] = pack_key(score, static_cast<uint32_t>(P.cand_base + lv.cand_off + w.a * lv.hw + w.pos0 + 4 * t + i), static_cast<uint32_t>(cid));
+                        okm |= 1u << i;
+                        const uint32_t sb = __float_as_uint(score);
+                        smax_bits = max(smax_bits, sb);
+                        smin_inv = max(smin_inv, ~sb);
+                    }
+                }
+            }
+            emit_keys<4>(out, okm, npre, smax_bits, smin_inv, keys + static_cast<int64_t>(w.img) * key_cap, key_cap,
+                         counts + w.img * 4, P.pre_kind == PRE_ANY_GT);
+        }
+    }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda at link time)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// the TMA variant covers heads whose streamed channels are contiguous: objectness right before class 0, or none
+static bool tma_variant_applies(const Plan &P, int vec)
+{
+    if (P.layout != LAYOUT_PLANES || vec != 4 || P.multi_label) return false;
+    if (P.use_obj && !(P.obj_src == 0 && P.obj_nch == P.cls_nch && P.obj_ch == P.cls_ch - 1)) return false;
+    return encode_tiled_fn() != nullptr;
+}
+
+template <int CW, int PL, int BPS>
+static cudaError_t launch_tma(const Plan &P, int num_sms, uint64_t *d_keys, int64_t key_cap, int32_t *d_counts, cudaStream_t stream)
+{
+    constexpr int kItemPos = 128 * CW;
+    constexpr int kThreads = (CW + 1) * 32;
+    static_assert(CW % 2 == 0 && CW / 2 <= 32, "one producer lane per 256-position request");
+    TmaCfg cfg;
+    TmaMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    cfg.obj_first = P.use_obj ? 1 : 0;
+    cfg.nq = P.C + cfg.obj_first;
+    cfg.row0 = P.cls_ch - cfg.obj_first;
+    const size_t stage_bytes = static_cast<size_t>(PL) * kItemPos * sizeof(float);
+    int stages = static_cast<int>(((216 / BPS) * 1024) / stage_bytes);
+    stages = stages > 16 ? 16 : (stages < 2 ? 2 : stages);
+    cfg.stages = stages;
+    int items = 0;
+    EncodeTiledFn enc = encode_tiled_fn();
+    for (int l = 0; l < P.L; ++l) {
+        const LevelDesc &lv = P.lv[l];
+        cfg.item_off[l] = items;
+        cfg.blocks_per_anchor[l] = (lv.hw + kItemPos - 1) / kItemPos;
+        cfg.box0[l] = lv.hw < 256 ? lv.hw : 256;
+        items += P.A * cfg.blocks_per_anchor[l];
+        const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(lv.hw), static_cast<cuuint64_t>(P.batch) * P.A * P.cls_nch};
+        const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(lv.hw) * sizeof(float)};
+        const cuuint32_t box[2] = {static_cast<cuuint32_t>(cfg.box0[l]), static_cast<cuuint32_t>(PL)};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = enc(&maps.m[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(lv.p0), gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    }
+    for (int l = P.L; l < YSB_MAX_LEVELS; ++l) { cfg.item_off[l] = items; cfg.blocks_per_anchor[l] = 1; cfg.box0[l] = 256; }
+    cfg.items_per_img = items;
+    const int total = items * P.batch;
+    const size_t smem = stage_bytes * stages + 2 * sizeof(uint64_t) * stages + 128;
+    cudaError_t e = cudaFuncSetAttribute(k_filter_planes_tma<CW, PL, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    const int grid = total < num_sms * BPS ? total : num_sms * BPS;
+    k_filter_planes_tma<CW, PL, BPS><<<grid, kThreads, smem, stream>>>(P, cfg, maps, total, d_keys, key_cap, d_counts);
     return cudaGetLastError();
 }
 
@@ -943,7 +1178,24 @@ cudaError_t launch_filter(const Plan &P, int vec, uint64_t *d_keys, int64_t key_
         k_filter_multilabel<<<grid, 256, 0, stream>>>(P, d_keys, key_cap, d_counts);
         return cudaGetLastError();
     }
-    if (P.layout == LAYOUT_PLANES && vec == 4 && g_filter_variant != 1) {  // ring variants need every level vectorised
+    if (g_filter_variant == 3 && tma_variant_applies(P, vec)) {  // 2-D tensor-map TMA ring
+        int num_sms = 0, dev = 0;
+        e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        const bool nine = (P.C + (P.use_obj ? 1 : 0)) % 9 == 0;
+        switch (g_bulk_ppt) {
+        case 4: return nine ? launch_tma<4, 9, 2>(P, num_sms, d_keys, key_cap, d_counts, stream) : launch_tma<4, 8, 2>(P, num_sms, d_keys, key_cap, d_counts, stream);
+        case 2: return nine ? launch_tma<2, 9, 4>(P, num_sms, d_keys, key_cap, d_counts, stream) : launch_tma<2, 8, 4>(P, num_sms, d_keys, key_cap, d_counts, stream);
+        case 163: return nine ? launch_tma<16, 3, 1>(P, num_sms, d_keys, key_cap, d_counts, stream) : launch_tma<16, 4, 1>(P, num_sms, d_keys, key_cap, d_counts, stream);
+        case 83: return nine ? launch_tma<8, 3, 2>(P, num_sms, d_keys, key_cap, d_counts, stream) : launch_tma<8, 4, 2>(P, num_sms, d_keys, key_cap, d_counts, stream);
+        case 43: return nine ? launch_tma<4, 3, 4>(P, num_sms, d_keys, key_cap, d_counts, stream) : launch_tma<4, 4, 4>(P, num_sms, d_keys, key_cap, d_counts, stream);
+        case 16: return nine ? launch_tma<16, 9, 1>(P, num_sms, d_keys, key_cap, d_counts, stream) : launch_tma<16, 8, 1>(P, num_sms, d_keys, key_cap, d_counts, stream);
+        default: return nine ? launch_tma<8, 9, 1>(P, num_sms, d_keys, key_cap, d_counts, stream) : launch_tma<8, 8, 1>(P, num_sms, d_keys, key_cap, d_counts, stream);
+        }
+    }
+    if (P.layout == LAYOUT_PLANES && vec == 4 && g_filter_variant != 1 && g_filter_variant != 3) {  // ring variants need every level vectorised
         int num_sms = 0, dev = 0;
         e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
