@@ -16,6 +16,7 @@
  *   ysb_postprocess       XEvaluator.__call__ minus model  trainer/eval_yolov5.py:30-42
  *   ysb_postprocess_tta   the same with hyp['use_tta']     trainer/eval_yolov5.py:30-42 + 152-179 (test_time_augmentation)
  *   ysb_decode_into       one pass of test_time_augmentation (decode + scale/flip undo + concat slot)
+ *   ysb_elementwise_iou_backward  autograd of the three      loss/yolov5_loss.py:110, yolov7_loss.py:130, yolov8_loss.py:306
  *   ysb_soft_nms          utils.gpu_*_soft_nms             utils/nms.py:68-140
  *   ysb_undo_letterbox    box half of preds_postprocess    val_yolov5.py:166-172
  *   ysb_nms               utils.numba_nms / utils.gpu_nms  utils/nms.py:10-27 / 30-65
@@ -184,6 +185,14 @@ int ysb_nms_workspace_bytes(int64_t m, size_t *bytes_out);
 int ysb_nms(const float *d_boxes, const float *d_scores, int64_t m, double iou_thr, int cmp, int iou_kind,
             int64_t max_keep, void *d_workspace, size_t workspace_bytes, int32_t *d_keep, int32_t *d_keep_cnt,
             void *stream);
+
+/* Backward of ysb_elementwise_iou for the loss-side callers that differentiate through gpu_CIoU (loss/yolov5_loss.py:110,
+ * loss/yolov7_loss.py:130, loss/yolov8_loss.py:306, loss/loss.py:109) / gpu_Giou / gpu_DIoU: given d_grad_out (n2) it
+ * writes dL/d_b2 (n2,4) and dL/d_b1 (n1,4; summed over the rows when n1 == 1).  Either gradient pointer may be NULL.
+ * torch's sub-gradient conventions (ties of max/min split evenly, clamp passes the gradient on its bounds, alpha of CIoU
+ * constant).  float32 throughout. */
+int ysb_elementwise_iou_backward(const float *d_b1, int64_t n1, const float *d_b2, int64_t n2, int iou_kind,
+                                 const float *d_grad_out, float *d_grad_b1, float *d_grad_b2, void *stream);
 
 /* Soft-NMS (utils/nms.py:68-140; no caller in the reference, float32 GIoU/DIoU/CIoU flavours only -- 'iou' is broken
  * there).  Repeats: pick the first arg-max, record processed[idx] = its current score, decay every score whose IoU with

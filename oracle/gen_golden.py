@@ -180,6 +180,25 @@ def utils_case(utils):
         store[f"tnms_{kind}"] = np.asarray(utils.gpu_nms(b2, sc, kind, 0.45), dtype=np.int32)
     store["tnms_scores"] = sc.numpy()
     store["anchors_64x96"] = utils.GPUAnchor([64, 96])().cpu().numpy()
+    # autograd through the row-wise IoU flavours (the loss-side callers, loss/yolov5_loss.py:110): d(sum(w * iou))/d boxes
+    ga = b1[:64].clone()
+    gb = b2[:64].clone()
+    gb[0, 0] = ga[0, 0]                      # tie in max(x1, x1'): torch splits the gradient evenly
+    gb[1] = ga[1]                            # identical boxes: every max/min ties
+    gb[2, 2] = ga[2, 2]
+    gb[3] = ga[3] + 500.0                    # disjoint: intersection clamped at 0
+    gb[4, 0] = ga[4, 2]                      # touching: clamp input exactly 0 (gradient still passes)
+    gb[4, 2] = gb[4, 0] + 10.0
+    wts = torch.from_numpy(rng.uniform(-1, 1, size=64).astype(np.float32))
+    store["grad_b1"], store["grad_b2"], store["grad_w"] = ga.numpy().copy(), gb.numpy().copy(), wts.numpy()
+    for kind, fn in (("giou", utils.gpu_Giou), ("diou", utils.gpu_DIoU), ("ciou", utils.gpu_CIoU)):
+        x1, x2 = ga.clone().requires_grad_(True), gb.clone().requires_grad_(True)
+        (fn(x1, x2) * wts).sum().backward()
+        store[f"grad_{kind}_d1"], store[f"grad_{kind}_d2"] = x1.grad.numpy(), x2.grad.numpy()
+    for kind, fn in (("giou", utils.gpu_Giou), ("diou", utils.gpu_DIoU)):      # box1 broadcast over the rows
+        x1, x2 = ga[:1].clone().requires_grad_(True), gb.clone().requires_grad_(True)
+        (fn(x1, x2) * wts).sum().backward()
+        store[f"grad_{kind}_row_d1"], store[f"grad_{kind}_row_d2"] = x1.grad.numpy(), x2.grad.numpy()
     # soft-NMS (utils/nms.py:68-140): dead code in the reference, runs for the giou/diou/ciou flavours with (M,1) scores
     m = 48
     sb = b2[:m].clone()

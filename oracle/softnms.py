@@ -101,3 +101,97 @@ def undo_letterbox(rows, scale, pad_top, pad_left, org_h, org_w):
     out[:, [0, 2]] = np.clip((out[:, [0, 2]] - F(pad_left)) / F(scale), F(1), F(org_w - 1))
     out[:, [1, 3]] = np.clip((out[:, [1, 3]] - F(pad_top)) / F(scale), F(1), F(org_h - 1))
     return out
+
+
+# ---- backward of the row-wise flavours (torch autograd of utils/bbox_tools.py:193-339, restated analytically) -----------
+def _split_max(p, q, g):
+    """d max(p, q): torch.maximum sends the whole gradient to the larger input and half to each at a tie."""
+    wp = np.where(p > q, 1.0, np.where(p == q, 0.5, 0.0))
+    return g * wp, g * (1.0 - wp)
+
+
+def _split_min(p, q, g):
+    wp = np.where(p < q, 1.0, np.where(p == q, 0.5, 0.0))
+    return g * wp, g * (1.0 - wp)
+
+
+def iou_backward(kind, b1, b2, grad_out):
+    """d sum(grad_out * flavour(b1, b2)) / d b1, d b2 in float64 on float32 inputs; b1 (1,4) is broadcast and its
+    gradient summed.  clamp passes the gradient on its bounds, abs'(0) = 0, CIoU's alpha is a constant (:334-335)."""
+    a = np.asarray(b1, dtype=np.float64).reshape(-1, 4)
+    b = np.asarray(b2, dtype=np.float64).reshape(-1, 4)
+    G = np.asarray(grad_out, dtype=np.float64).reshape(-1)
+    bc = a.shape[0] == 1 and b.shape[0] != 1
+    if bc:
+        a = np.repeat(a, b.shape[0], axis=0)
+    eps_u = 1e-9 if kind == "ciou" else 1e-6
+    w1, h1, w2, h2 = a[:, 2] - a[:, 0], a[:, 3] - a[:, 1], b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]
+    tw = np.minimum(a[:, 2], b[:, 2]) - np.maximum(a[:, 0], b[:, 0])
+    th = np.minimum(a[:, 3], b[:, 3]) - np.maximum(a[:, 1], b[:, 1])
+    iw, ih = np.maximum(tw, 0.0), np.maximum(th, 0.0)
+    inter = iw * ih
+    u_raw = w1 * h1 + w2 * h2 - inter
+    uc = np.maximum(u_raw, eps_u)
+    iou = inter / uc
+    cw = np.maximum(a[:, 2], b[:, 2]) - np.minimum(a[:, 0], b[:, 0])
+    ch = np.maximum(a[:, 3], b[:, 3]) - np.minimum(a[:, 1], b[:, 1])
+    z = np.zeros_like(G)
+    d_uraw, d_cw, d_ch, d_w1, d_h1, d_w2, d_h2, d_dx, d_dy = (z.copy() for _ in range(9))
+    if kind == "giou":
+        C = cw * ch
+        cc = np.maximum(C, 1e-6)
+        diff = C - u_raw
+        d_iou = G
+        d_diff = (-G / np.abs(cc)) * np.sign(diff)
+        d_C = d_diff + np.where(C >= 1e-6, (G * np.abs(diff) / cc ** 2) * np.sign(cc), 0.0)
+        d_uraw = d_uraw - d_diff
+        d_cw, d_ch = d_C * ch, d_C * cw
+    else:
+        eps_c = 1e-9 if kind == "ciou" else 1e-6
+        c2 = cw * cw + ch * ch
+        c2c = np.maximum(c2, eps_c)
+        dx = (a[:, 2] + a[:, 0]) / 2 - (b[:, 2] + b[:, 0]) / 2
+        dy = (a[:, 3] + a[:, 1]) / 2 - (b[:, 3] + b[:, 1]) / 2
+        rho2 = dx * dx + dy * dy
+        g_pre = G.copy()
+        if kind == "diou":
+            pre = iou - rho2 / c2c
+            g_pre = np.where((pre >= -1) & (pre <= 1), G, 0.0)
+        d_iou = g_pre
+        d_c2 = np.where(c2 >= eps_c, g_pre * rho2 / c2c ** 2, 0.0)
+        d_cw, d_ch = 2 * cw * d_c2, 2 * ch * d_c2
+        d_dx, d_dy = 2 * dx * (-g_pre / c2c), 2 * dy * (-g_pre / c2c)
+        if kind == "ciou":
+            h1c, h2c = np.maximum(h1, 1e-9), np.maximum(h2, 1e-9)
+            r1, r2 = w1 / h1c, w2 / h2c
+            delta = np.arctan(r1) - np.arctan(r2)
+            k = 4 / np.pi ** 2
+            v = k * delta ** 2
+            alpha = v / np.maximum(1 - iou + v, 1e-9)
+            d_delta = (-g_pre * alpha) * k * 2 * delta
+            d_r1, d_r2 = d_delta / (1 + r1 * r1), -d_delta / (1 + r2 * r2)
+            d_w1 = d_w1 + d_r1 / h1c
+            d_h1 = d_h1 + np.where(h1 >= 1e-9, -d_r1 * w1 / h1c ** 2, 0.0)
+            d_w2 = d_w2 + d_r2 / h2c
+            d_h2 = d_h2 + np.where(h2 >= 1e-9, -d_r2 * w2 / h2c ** 2, 0.0)
+    d_inter = d_iou / uc
+    d_uraw = d_uraw + np.where(u_raw >= eps_u, -d_iou * inter / uc ** 2, 0.0)
+    d_w1, d_h1 = d_w1 + d_uraw * h1, d_h1 + d_uraw * w1
+    d_w2, d_h2 = d_w2 + d_uraw * h2, d_h2 + d_uraw * w2
+    d_inter = d_inter - d_uraw
+    d_tw = np.where(tw >= 0, d_inter * ih, 0.0)
+    d_th = np.where(th >= 0, d_inter * iw, 0.0)
+    ga = np.stack([-d_w1 + d_dx / 2, -d_h1 + d_dy / 2, d_w1 + d_dx / 2, d_h1 + d_dy / 2], axis=1)
+    gb = np.stack([-d_w2 - d_dx / 2, -d_h2 - d_dy / 2, d_w2 - d_dx / 2, d_h2 - d_dy / 2], axis=1)
+    for col_lo, col_hi, d_t, d_c in ((0, 2, d_tw, d_cw), (1, 3, d_th, d_ch)):
+        p, q = _split_max(a[:, col_lo], b[:, col_lo], -d_t)     # intersection low edge = max
+        ga[:, col_lo] += p; gb[:, col_lo] += q
+        p, q = _split_min(a[:, col_hi], b[:, col_hi], d_t)      # intersection high edge = min
+        ga[:, col_hi] += p; gb[:, col_hi] += q
+        p, q = _split_min(a[:, col_lo], b[:, col_lo], -d_c)     # enclosing low edge = min
+        ga[:, col_lo] += p; gb[:, col_lo] += q
+        p, q = _split_max(a[:, col_hi], b[:, col_hi], d_c)      # enclosing high edge = max
+        ga[:, col_hi] += p; gb[:, col_hi] += q
+    if bc:
+        ga = ga.sum(axis=0, keepdims=True)
+    return ga, gb

@@ -158,6 +158,59 @@ def test_torch_iou_family_matches_reference():
         gpu_nms(g["tiou_b2"], sc, "iou", 0.45)
 
 
+def test_rowwise_iou_autograd_matches_reference():
+    """gpu_Giou / gpu_DIoU / gpu_CIoU under autograd (ysb_elementwise_iou_backward) vs torch autograd through the
+    reference's own functions: |d - ref| <= 1e-5 * max(|ref|, 1) (float32 chain; the golden gradients are O(0.1))."""
+    from yoloseries_b200.utils import gpu_CIoU, gpu_DIoU, gpu_Giou, gpu_iou
+    g = load_golden("utils_nms_iou")
+    w = torch.from_numpy(g["grad_w"]).cuda()
+    worst = 0.0
+    for kind, fn in (("giou", gpu_Giou), ("diou", gpu_DIoU), ("ciou", gpu_CIoU)):
+        x1 = torch.from_numpy(g["grad_b1"]).cuda().requires_grad_(True)
+        x2 = torch.from_numpy(g["grad_b2"]).cuda().requires_grad_(True)
+        out = fn(x1, x2)
+        assert out.requires_grad and out.shape == (64,)
+        (out * w).sum().backward()
+        for got, key in ((x1.grad, f"grad_{kind}_d1"), (x2.grad, f"grad_{kind}_d2")):
+            err = np.abs(got.cpu().numpy() - g[key])
+            worst = max(worst, float(err.max()))
+            assert close_rel(got.cpu().numpy(), g[key], 1e-5).all(), (key, err.max())
+    for kind, fn in (("giou", gpu_Giou), ("diou", gpu_DIoU)):      # broadcast box1: gradient summed over the rows
+        x1 = torch.from_numpy(g["grad_b1"][:1]).cuda().requires_grad_(True)
+        x2 = torch.from_numpy(g["grad_b2"]).cuda().requires_grad_(True)
+        (fn(x1, x2) * w).sum().backward()
+        assert x1.grad.shape == (1, 4)
+        assert close_rel(x1.grad.cpu().numpy(), g[f"grad_{kind}_row_d1"], 1e-5).all()
+        assert close_rel(x2.grad.cpu().numpy(), g[f"grad_{kind}_row_d2"], 1e-5).all()
+    assert worst <= 2e-6, worst                                       # in practice far inside the stated tolerance
+    # only one side needs a gradient (the loss case: targets are constants); CPU leaves get CPU gradients
+    x1 = torch.from_numpy(g["grad_b1"]).requires_grad_(True)
+    x2 = torch.from_numpy(g["grad_b2"])
+    gpu_CIoU(x1, x2).sum().backward()
+    assert x1.grad.device.type == "cpu" and x2.grad is None
+    ref1, _ = oracle.iou_backward("ciou", g["grad_b1"], g["grad_b2"], np.ones(64))
+    assert close_rel(x1.grad.numpy(), ref1, 1e-5).all()
+    # a larger random batch against the analytic oracle
+    rng = np.random.default_rng(3)
+    xy = rng.uniform(0, 600, size=(5000, 2)).astype(np.float32)
+    wh = rng.uniform(2, 200, size=(5000, 2)).astype(np.float32)
+    a = np.concatenate((xy, xy + wh), axis=1)
+    xy2 = xy + rng.normal(0, 20, size=(5000, 2)).astype(np.float32)
+    wh2 = (wh * np.exp(rng.normal(0, 0.4, size=(5000, 2)))).astype(np.float32)
+    b = np.concatenate((xy2, xy2 + wh2), axis=1).astype(np.float32)
+    go = rng.uniform(-1, 1, size=5000).astype(np.float32)
+    for kind, fn in (("giou", gpu_Giou), ("diou", gpu_DIoU), ("ciou", gpu_CIoU)):
+        x1, x2 = torch.from_numpy(a).cuda().requires_grad_(True), torch.from_numpy(b).cuda().requires_grad_(True)
+        fn(x1, x2).backward(torch.from_numpy(go).cuda())
+        r1, r2 = oracle.iou_backward(kind, a, b, go)
+        assert close_rel(x1.grad.cpu().numpy(), r1, 1e-5).all() and close_rel(x2.grad.cpu().numpy(), r2, 1e-5).all()
+    # no_grad / detached inputs take the plain forward; the pairwise gpu_iou refuses to be differentiated
+    with torch.no_grad():
+        assert not gpu_CIoU(x1, x2).requires_grad
+    with pytest.raises(NotImplementedError):
+        gpu_iou(x1, x2)
+
+
 def test_soft_nms_matches_reference():
     """utils/nms.py:68-140 through ysb_soft_nms: the reference's own keep masks, and the oracle on a larger set."""
     from yoloseries_b200.utils import gpu_exponential_soft_nms, gpu_linear_soft_nms

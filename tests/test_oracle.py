@@ -192,3 +192,17 @@ def test_tta_merge_and_rows_match_reference(name):
             assert close_rel(r.rows[:, :4], want[:, :4], 1e-5).all()
         else:
             np.testing.assert_array_equal(r.rows, want)
+
+
+def test_iou_backward_matches_reference_autograd():
+    """Analytic backward of GIoU / DIoU / CIoU (oracle/softnms.py::iou_backward) vs torch autograd through the reference's
+    own functions, including ties of max/min, disjoint and touching boxes, and the broadcast box1."""
+    g = load_golden("utils_nms_iou")
+    b1, b2, w = g["grad_b1"], g["grad_b2"], g["grad_w"]
+    for kind in ("giou", "diou", "ciou"):
+        d1, d2 = oracle.iou_backward(kind, b1, b2, w)
+        assert np.abs(d1 - g[f"grad_{kind}_d1"]).max() <= 2e-7 and np.abs(d2 - g[f"grad_{kind}_d2"]).max() <= 2e-7
+    for kind in ("giou", "diou"):
+        d1, d2 = oracle.iou_backward(kind, b1[:1], b2, w)
+        assert d1.shape == (1, 4)
+        assert np.abs(d1 - g[f"grad_{kind}_row_d1"]).max() <= 2e-7 and np.abs(d2 - g[f"grad_{kind}_row_d2"]).max() <= 2e-7

@@ -28,6 +28,8 @@ cudaError_t launch_elementwise_iou(const float *b1, int64_t n1, const float *b2,
 cudaError_t debug_k2_timing(long long *host_out);
 #endif
 
+cudaError_t launch_elementwise_iou_backward(const float *b1, int64_t n1, const float *b2, int64_t n2, int kind,
+                                            const float *grad_out, float *g1, float *g2, cudaStream_t stream);
 cudaError_t launch_soft_nms(const float *boxes, const float *scores, int64_t m, float thr, int kind, int mode, float sigma,
                             void *ws, float *processed, cudaStream_t stream);
 cudaError_t launch_undo_letterbox(float *dets, const int32_t *cnt, int batch, int max_det, const float *info, cudaStream_t stream);
@@ -458,6 +460,16 @@ int ysb_nms(const float *d_boxes, const float *d_scores, int64_t m, double iou_t
     if (workspace_bytes < array_nms_workspace_bytes(m)) return YSB_ERR_WORKSPACE;
     return cuda_status(launch_array_nms(d_boxes, d_scores, m, iou_thr, cmp, iou_kind, max_keep, d_workspace, d_keep,
                                         d_keep_cnt, static_cast<cudaStream_t>(stream)));
+}
+
+int ysb_elementwise_iou_backward(const float *d_b1, int64_t n1, const float *d_b2, int64_t n2, int iou_kind,
+                                 const float *d_grad_out, float *d_grad_b1, float *d_grad_b2, void *stream)
+{
+    if (n1 < 0 || n2 < 0 || (n2 > 0 && (!d_b1 || !d_b2 || !d_grad_out))) return YSB_ERR_BAD_ARG;
+    if (n1 != n2 && n1 != 1) return YSB_ERR_BAD_ARG;
+    if (iou_kind != YSB_GIOU && iou_kind != YSB_DIOU && iou_kind != YSB_CIOU) return YSB_ERR_BAD_ARG;
+    return cuda_status(launch_elementwise_iou_backward(d_b1, n1, d_b2, n2, iou_kind, d_grad_out, d_grad_b1, d_grad_b2,
+                                                       static_cast<cudaStream_t>(stream)));
 }
 
 int ysb_soft_nms(const float *d_boxes, const float *d_scores, int64_t m, float iou_thr, int iou_kind, int mode,

@@ -32,6 +32,172 @@ __global__ void __launch_bounds__(256) k_elementwise_iou(const float4 *__restric
     out[j] = iou_kind_f32(kind, __ldg(b1 + (n1 == 1 ? 0 : j)), __ldg(b2 + j));
 }
 
+// ---- backward of the row-wise GIoU / DIoU / CIoU (the loss-side callers: loss/yolov5_loss.py:110, yolov7_loss.py:130,
+// yolov8_loss.py:306, loss.py:109 differentiate through gpu_CIoU) -----------------------------------------------------
+// Reverse-mode walk of the torch graph of utils/bbox_tools.py:193-339 with torch's sub-gradient conventions:
+// maximum/minimum split the gradient evenly at ties, clamp passes it where the input is inside [min, max] (bounds
+// included), abs uses sign(x) (0 at 0); alpha of CIoU is a constant (computed under no_grad, :334-335).
+struct Grad4 {
+    float x1, y1, x2, y2;
+};
+__device__ __forceinline__ void max_bwd(float p, float q, float g, float &gp, float &gq)
+{
+    const float wp = p > q ? 1.0f : (p == q ? 0.5f : 0.0f);
+    gp += g * wp;
+    gq += g * (1.0f - wp);
+}
+__device__ __forceinline__ void min_bwd(float p, float q, float g, float &gp, float &gq)
+{
+    const float wp = p < q ? 1.0f : (p == q ? 0.5f : 0.0f);
+    gp += g * wp;
+    gq += g * (1.0f - wp);
+}
+
+__device__ __forceinline__ void iou_kind_backward(int kind, float4 a, float4 b, float G, Grad4 &ga, Grad4 &gb)
+{
+    const float eps_u = kind == YSB_CIOU ? 1e-9f : 1e-6f;  // clamp of the union (:308 / :216, :260)
+    const float w1 = a.z - a.x, h1 = a.w - a.y, w2 = b.z - b.x, h2 = b.w - b.y;
+    const float ix1 = fmaxf(a.x, b.x), iy1 = fmaxf(a.y, b.y), ix2 = fminf(a.z, b.z), iy2 = fminf(a.w, b.w);
+    const float tw = ix2 - ix1, th = iy2 - iy1;
+    const float iw = fmaxf(tw, 0.0f), ih = fmaxf(th, 0.0f);
+    const float inter = iw * ih;
+    const float u_raw = w1 * h1 + w2 * h2 - inter;
+    const float uc = fmaxf(u_raw, eps_u);
+    const float iou = inter / uc;
+    const float cx1 = fminf(a.x, b.x), cy1 = fminf(a.y, b.y), cx2 = fmaxf(a.z, b.z), cy2 = fmaxf(a.w, b.w);
+    const float cw = cx2 - cx1, ch = cy2 - cy1;
+
+    float d_iou = 0.0f, d_uraw = 0.0f, d_cw = 0.0f, d_ch = 0.0f;
+    float d_w1 = 0.0f, d_h1 = 0.0f, d_w2 = 0.0f, d_h2 = 0.0f;
+    float d_dx = 0.0f, d_dy = 0.0f;  // centre differences (box1 - box2)
+    if (kind == YSB_GIOU) {
+        // g = iou - |C - U| / |clamp(C, 1e-6)|
+        const float C = cw * ch;
+        const float cc = fmaxf(C, 1e-6f);
+        const float diff = C - u_raw;
+        const float num = fabsf(diff), den = fabsf(cc);
+        d_iou = G;
+        const float d_num = -G / den, d_den = G * num / (den * den);
+        const float sgn = diff > 0.0f ? 1.0f : (diff < 0.0f ? -1.0f : 0.0f);
+        const float d_diff = d_num * sgn;
+        float d_C = d_diff;
+        d_uraw += -d_diff;
+        const float d_cc = d_den * (cc > 0.0f ? 1.0f : (cc < 0.0f ? -1.0f : 0.0f));
+        if (C >= 1e-6f) d_C += d_cc;
+        d_cw += d_C * ch;
+        d_ch += d_C * cw;
+    } else {
+        // DIoU: clamp(iou - rho2 / clamp(c2, 1e-6), -1, 1);  CIoU: iou - (rho2 / clamp(c2, 1e-9) + v * alpha)
+        const float eps_c = kind == YSB_CIOU ? 1e-9f : 1e-6f;
+        const float c2 = cw * cw + ch * ch;
+        const float c2c = fmaxf(c2, eps_c);
+        const float dx = (a.z + a.x) * 0.5f - (b.z + b.x) * 0.5f;
+        const float dy = (a.w + a.y) * 0.5f - (b.w + b.y) * 0.5f;
+        const float rho2 = dx * dx + dy * dy;
+        float g_pre = G;
+        float v = 0.0f, alpha = 0.0f, delta = 0.0f, r1 = 0.0f, r2 = 0.0f, h1c = 1.0f, h2c = 1.0f;
+        if (kind == YSB_DIOU) {
+            const float pre = iou - rho2 / c2c;
+            if (!(pre >= -1.0f && pre <= 1.0f)) g_pre = 0.0f;
+        } else {
+            h1c = fmaxf(h1, 1e-9f);
+            h2c = fmaxf(h2, 1e-9f);
+            r1 = w1 / h1c;
+            r2 = w2 / h2c;
+            delta = atanf(r1) - atanf(r2);
+            v = 0.40528473456935109f * (delta * delta);
+            alpha = v / fmaxf(1.0f - iou + v, 1e-9f);
+        }
+        d_iou = g_pre;
+        const float d_pen = -g_pre;
+        const float d_rho2 = d_pen / c2c;
+        const float d_c2c = -d_pen * rho2 / (c2c * c2c);
+        const float d_c2 = c2 >= eps_c ? d_c2c : 0.0f;
+        d_cw += 2.0f * cw * d_c2;
+        d_ch += 2.0f * ch * d_c2;
+        d_dx = 2.0f * dx * d_rho2;
+        d_dy = 2.0f * dy * d_rho2;
+        if (kind == YSB_CIOU) {
+            const float d_v = -g_pre * alpha;
+            const float d_delta = d_v * 0.40528473456935109f * 2.0f * delta;
+            const float d_r1 = d_delta / (1.0f + r1 * r1), d_r2 = -d_delta / (1.0f + r2 * r2);
+            d_w1 += d_r1 / h1c;
+            if (h1 >= 1e-9f) d_h1 += -d_r1 * w1 / (h1c * h1c);
+            d_w2 += d_r2 / h2c;
+            if (h2 >= 1e-9f) d_h2 += -d_r2 * w2 / (h2c * h2c);
+        }
+    }
+    // iou = inter / clamp(u_raw, eps)
+    float d_inter = d_iou / uc;
+    const float d_uc = -d_iou * inter / (uc * uc);
+    if (u_raw >= eps_u) d_uraw += d_uc;
+    d_w1 += d_uraw * h1;
+    d_h1 += d_uraw * w1;
+    d_w2 += d_uraw * h2;
+    d_h2 += d_uraw * w2;
+    d_inter -= d_uraw;
+    const float d_tw = tw >= 0.0f ? d_inter * ih : 0.0f;
+    const float d_th = th >= 0.0f ? d_inter * iw : 0.0f;
+    // leaves
+    ga = Grad4{-d_w1 + 0.5f * d_dx, -d_h1 + 0.5f * d_dy, d_w1 + 0.5f * d_dx, d_h1 + 0.5f * d_dy};
+    gb = Grad4{-d_w2 - 0.5f * d_dx, -d_h2 - 0.5f * d_dy, d_w2 - 0.5f * d_dx, d_h2 - 0.5f * d_dy};
+    max_bwd(a.x, b.x, -d_tw, ga.x1, gb.x1);  // ix1 = max(ax1, bx1), tw = ix2 - ix1
+    min_bwd(a.z, b.z, d_tw, ga.x2, gb.x2);   // ix2 = min(ax2, bx2)
+    max_bwd(a.y, b.y, -d_th, ga.y1, gb.y1);
+    min_bwd(a.w, b.w, d_th, ga.y2, gb.y2);
+    min_bwd(a.x, b.x, -d_cw, ga.x1, gb.x1);  // cx1 = min, cw = cx2 - cx1
+    max_bwd(a.z, b.z, d_cw, ga.x2, gb.x2);
+    min_bwd(a.y, b.y, -d_ch, ga.y1, gb.y1);
+    max_bwd(a.w, b.w, d_ch, ga.y2, gb.y2);
+}
+
+__global__ void __launch_bounds__(256) k_elementwise_iou_backward(const float4 *__restrict__ b1, int64_t n1,
+                                                                  const float4 *__restrict__ b2, int64_t n2, int kind,
+                                                                  const float *__restrict__ grad_out, float4 *__restrict__ g1,
+                                                                  float4 *__restrict__ g2)
+{
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    Grad4 ga{0.f, 0.f, 0.f, 0.f}, gb{0.f, 0.f, 0.f, 0.f};
+    if (j < n2) {
+        iou_kind_backward(kind, __ldg(b1 + (n1 == 1 ? 0 : j)), __ldg(b2 + j), __ldg(grad_out + j), ga, gb);
+        if (g2) g2[j] = make_float4(gb.x1, gb.y1, gb.x2, gb.y2);
+    }
+    if (!g1) return;
+    if (n1 != 1) {
+        if (j < n2) g1[j] = make_float4(ga.x1, ga.y1, ga.x2, ga.y2);
+        return;
+    }
+    // broadcast box1: sum over the rows (warp shuffle, then one atomic per warp and component; g1 zeroed by the launcher)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        ga.x1 += __shfl_xor_sync(0xffffffffu, ga.x1, d);
+        ga.y1 += __shfl_xor_sync(0xffffffffu, ga.y1, d);
+        ga.x2 += __shfl_xor_sync(0xffffffffu, ga.x2, d);
+        ga.y2 += __shfl_xor_sync(0xffffffffu, ga.y2, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        float *o = reinterpret_cast<float *>(g1);
+        atomicAdd(o + 0, ga.x1);
+        atomicAdd(o + 1, ga.y1);
+        atomicAdd(o + 2, ga.x2);
+        atomicAdd(o + 3, ga.y2);
+    }
+}
+
+cudaError_t launch_elementwise_iou_backward(const float *b1, int64_t n1, const float *b2, int64_t n2, int kind,
+                                            const float *grad_out, float *g1, float *g2, cudaStream_t stream)
+{
+    if (n2 == 0) return cudaSuccess;
+    if (g1 && n1 == 1) {
+        cudaError_t e = cudaMemsetAsync(g1, 0, 4 * sizeof(float), stream);
+        if (e != cudaSuccess) return e;
+    }
+    k_elementwise_iou_backward<<<static_cast<unsigned>((n2 + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const float4 *>(b1), n1, reinterpret_cast<const float4 *>(b2), n2, kind, grad_out,
+        reinterpret_cast<float4 *>(g1), reinterpret_cast<float4 *>(g2));
+    return cudaGetLastError();
+}
+
 // ---- soft-NMS, utils/nms.py:68-140: one CTA, one pick per iteration (block arg-max + decay sweep) -----------------
 __global__ void __launch_bounds__(1024, 1) k_soft_nms(const float4 *__restrict__ boxes, const float *__restrict__ scores_in,
                                                       int m, float thr, int kind, int mode, float sigma, long long cap,

@@ -1,4 +1,9 @@
-"""Drop-in mirrors of the IoU routines of utils/bbox_tools.py; compute runs in libysb_postproc.so (forward only)."""
+"""Drop-in mirrors of the IoU routines of utils/bbox_tools.py; compute runs in libysb_postproc.so.
+
+The row-wise GIoU / DIoU / CIoU are differentiable (torch.autograd.Function over ysb_elementwise_iou /
+ysb_elementwise_iou_backward) because the reference's losses differentiate through them (loss/yolov5_loss.py:110,
+loss/yolov7_loss.py:130, loss/yolov8_loss.py:306, loss/loss.py:109).  Every caller of the pairwise gpu_iou runs under
+no_grad (loss/yolox_loss.py:92-133, loss/yolov7_loss.py:244-312), so that one stays forward-only."""
 import numpy as np
 import torch
 
@@ -11,8 +16,8 @@ __all__ = ["numba_iou", "gpu_iou", "gpu_Giou", "gpu_DIoU", "gpu_CIoU"]
 def _no_grad_only(*tensors):
     if any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
         raise NotImplementedError(
-            "the CUDA IoU kernels are forward-only; loss functions that differentiate through gpu_iou/gpu_CIoU "
-            "(loss/yolov5_loss.py:110, loss/yolox_loss.py:133) are outside the post-processing path (SURVEY.md 8f rank 4)")
+            "the pairwise gpu_iou kernel is forward-only: every caller in the reference runs it under no_grad "
+            "(loss/yolox_loss.py:92-133, loss/yolov7_loss.py:244-312); detach the inputs or wrap the call in torch.no_grad()")
 
 
 def numba_iou(bbox1, bbox2):
@@ -28,7 +33,8 @@ def numba_iou(bbox1, bbox2):
 
 def gpu_iou(bbox1, bbox2):
     """utils/bbox_tools.py:164-190 -- (N,4), (M,4) tensors -> (N,M) float32 tensor on the inputs' device."""
-    _no_grad_only(bbox1, bbox2)
+    if torch.is_grad_enabled():
+        _no_grad_only(bbox1, bbox2)
     b1, b2 = to_cuda_f32(bbox1.reshape(-1, 4)), to_cuda_f32(bbox2.reshape(-1, 4))
     out = torch.empty((b1.shape[0], b2.shape[0]), dtype=torch.float32, device=b1.device)
     with torch.cuda.device(b1.device):
@@ -37,20 +43,59 @@ def gpu_iou(bbox1, bbox2):
     return out
 
 
-def _rowwise(kind, bbox1, bbox2):
-    assert isinstance(bbox1, torch.Tensor)
-    assert isinstance(bbox2, torch.Tensor)
-    assert bbox1.shape[-1] == bbox2.shape[-1] == 4
-    assert bbox1.device == bbox2.device
-    _no_grad_only(bbox1, bbox2)
-    b1, b2 = to_cuda_f32(bbox1.reshape(-1, 4)), to_cuda_f32(bbox2.reshape(-1, 4))
-    if b1.shape[0] not in (1, b2.shape[0]):
-        raise RuntimeError(f"The size of tensor a ({b1.shape[0]}) must match the size of tensor b ({b2.shape[0]})")
+def _rowwise_forward(kind, b1, b2):
     out = torch.empty((b2.shape[0],), dtype=torch.float32, device=b2.device)
     with torch.cuda.device(b2.device):
         _lib.check(_lib.load().ysb_elementwise_iou(b1.data_ptr(), b1.shape[0], b2.data_ptr(), b2.shape[0], kind,
                                                    out.data_ptr(), stream_ptr()), "ysb_elementwise_iou")
     return out
+
+
+class _RowwiseIoU(torch.autograd.Function):
+    """forward: ysb_elementwise_iou; backward: ysb_elementwise_iou_backward (first order only)."""
+
+    @staticmethod
+    def forward(ctx, bbox1, bbox2, kind):
+        b1 = to_cuda_f32(bbox1.reshape(-1, 4))
+        b2 = to_cuda_f32(bbox2.reshape(-1, 4), b1.device)
+        ctx.save_for_backward(b1, b2)
+        ctx.kind = kind
+        ctx.meta = (bbox1.shape, bbox1.dtype, bbox1.device, bbox2.shape, bbox2.dtype, bbox2.device)
+        return _rowwise_forward(kind, b1, b2)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        b1, b2 = ctx.saved_tensors
+        shape1, dtype1, dev1, shape2, dtype2, dev2 = ctx.meta
+        need1, need2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        g = to_cuda_f32(grad_out.reshape(-1), b2.device)
+        g1 = torch.empty_like(b1) if need1 else None
+        g2 = torch.empty_like(b2) if need2 else None
+        with torch.cuda.device(b2.device):
+            _lib.check(_lib.load().ysb_elementwise_iou_backward(
+                b1.data_ptr(), b1.shape[0], b2.data_ptr(), b2.shape[0], ctx.kind, g.data_ptr(),
+                g1.data_ptr() if need1 else None, g2.data_ptr() if need2 else None, stream_ptr()),
+                "ysb_elementwise_iou_backward")
+        if need1:
+            g1 = g1.reshape(shape1).to(device=dev1, dtype=dtype1)
+        if need2:
+            g2 = g2.reshape(shape2).to(device=dev2, dtype=dtype2)
+        return g1, g2, None
+
+
+def _rowwise(kind, bbox1, bbox2):
+    assert isinstance(bbox1, torch.Tensor)
+    assert isinstance(bbox2, torch.Tensor)
+    assert bbox1.shape[-1] == bbox2.shape[-1] == 4
+    assert bbox1.device == bbox2.device
+    n1, n2 = bbox1.reshape(-1, 4).shape[0], bbox2.reshape(-1, 4).shape[0]
+    if n1 not in (1, n2):
+        raise RuntimeError(f"The size of tensor a ({n1}) must match the size of tensor b ({n2})")
+    if torch.is_grad_enabled() and (bbox1.requires_grad or bbox2.requires_grad):
+        return _RowwiseIoU.apply(bbox1, bbox2, kind)
+    b1, b2 = to_cuda_f32(bbox1.reshape(-1, 4)), to_cuda_f32(bbox2.reshape(-1, 4))
+    return _rowwise_forward(kind, b1, b2)
 
 
 def gpu_Giou(bbox1, bbox2):
