@@ -25,7 +25,6 @@ __all__ = ["YOLOV5Evaluator", "YOLOV7Evaluator", "YOLOXEvaluator", "YOLOV8Evalua
 
 class _Evaluator:
     family = None
-    _box_cols_xywh = True   # decoded rows carry [cx, cy, w, h] (True) or [x1, y1, x2, y2] (False) -- matters for TTA flips
 
     def _setup(self, model, hyp, compute_metric, anchors=None):
         self.hyp = hyp
@@ -96,9 +95,6 @@ class _Evaluator:
         merged, views = self._pp.decode_tta(self._tta_passes(inputs), (inputs.size(2), inputs.size(3)))
         return merged, views
 
-    def _pp_box_col(self):
-        return self.num_class if self.family.startswith("retinanet") else 0
-
     @staticmethod
     def scale_img(img, scale_factor):
         """trainer/eval_yolov5.py:211-227 (identical in every evaluator)."""
@@ -148,7 +144,6 @@ class YOLOXEvaluator(_Evaluator):
 
 class YOLOV8Evaluator(_Evaluator):
     family = "yolov8"
-    _box_cols_xywh = False
 
     def __init__(self, yolo, hyp, compute_metric=False):
         self.yolo = yolo
@@ -159,7 +154,6 @@ class YOLOV8Evaluator(_Evaluator):
 
 class RetinaNetEvaluator(_Evaluator):
     family = "retinanet"
-    _box_cols_xywh = False
 
     def __init__(self, model, hyp, compute_metric=False):
         self.model = model
@@ -186,7 +180,6 @@ class RetinaNetEvaluatorExperiment(RetinaNetEvaluator):
 
 class FCOSEvaluator(_Evaluator):
     family = "fcos"
-    _box_cols_xywh = False
 
     def __init__(self, model, hyp, compute_metric=False):
         self.model = model
