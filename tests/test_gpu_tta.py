@@ -183,6 +183,35 @@ def test_passes_with_different_geometry():
             np.testing.assert_array_equal(idx[i], wnt.cand_index)
 
 
+@pytest.mark.parametrize("fam", ["retinanet", "retinanet_exp", "fcos"])
+def test_tta_with_the_post_filter_window_active(fam):
+    """Few enough merged survivors (1 < M < 3000; FCOS <= 300) that postprocess_bbox runs over boxes decoded from all three
+    passes -- for RetinaNet including the score-weighted box merge (eval_retinanet.py:342-352)."""
+    from yoloseries_b200 import synth
+    from yoloseries_b200.engine import PostProcessor
+    C = 5
+    hyp = oracle.default_hyp(num_class=C)
+    img = 64
+    if fam == "fcos":
+        hyp.update(cls_threshold=0.55, iou_threshold=0.35, max_predictions_per_img=100)
+        img = 128
+    pp = PostProcessor(fam, hyp)
+    passes = [(synth.make_heads(fam, 3, img, img, C, "dense", seed=700 + k, device="cuda"), img, img, s, f)
+              for k, (s, f) in enumerate(zip(oracle.TTA_SCALES, oracle.TTA_FLIPS))]
+    merged, _ = pp.decode_tta(passes, (img, img))
+    want = oracle.evaluator_nms(fam, merged.cpu().numpy(), hyp)
+    rows, idx = pp.to_list(pp.run_tta(passes, (img, img)), as_numpy=True, with_index=True)
+    checked = 0
+    for i, wnt in enumerate(want):
+        if wnt.rows is None:
+            assert rows[i] is None
+            continue
+        _assert_rows_equal(fam, rows[i], wnt.rows)
+        np.testing.assert_array_equal(idx[i], wnt.cand_index)
+        checked += wnt.rows.shape[0]
+    assert checked > 0
+
+
 def test_full_size_tta_yolov5():
     """3 x 25 200 candidates per image (the reference's default validation path at 640x640)."""
     from yoloseries_b200 import synth
