@@ -120,3 +120,50 @@ def test_full_size_fused_vs_oracle(family, dist, img, batch, C):
         assert rows[i] is not None
         _assert_rows_equal(family, rows[i], w.rows)
         np.testing.assert_array_equal(idx[i], w.cand_index)
+
+
+@pytest.mark.parametrize("dist,pp_bbox", [("dense", True), ("crowd", True), ("crowd", False), ("sparse", False)])
+def test_bench_workload_properties(dist, pp_bbox):
+    """The bench workload at full size (64 YOLOv5s images, 1.6 M candidates) is too large for the CPU oracle, so check
+    the size-independent properties of the reference's result instead: rows sorted by score, at most max_det rows, every
+    row equal to the decoded candidate it names, no two kept boxes of one class with IoU >= thr (utils/nms.py:22), the
+    result is a fixed point of NMS (idempotence), and image i of the batch equals the same image run alone."""
+    from yoloseries_b200 import synth
+    from yoloseries_b200.engine import PostProcessor
+    from yoloseries_b200.utils import numba_iou, numba_nms
+    hyp = oracle.default_hyp(num_class=80, postprocess_bbox=pp_bbox)
+    heads = synth.make_heads("yolov5", 64, 640, 640, 80, dist, seed=1234, device="cuda")
+    pp = PostProcessor("yolov5", hyp, anchors=torch.tensor(synth.V5_ANCHORS_PX))
+    rows, idx = pp.to_list(pp.run(heads, 640, 640), as_numpy=True, with_index=True)
+    decoded = pp.decode(heads, 640, 640)
+    assert len(rows) == 64
+    seen = 0
+    for i in range(64):
+        r = rows[i]
+        if r is None:
+            continue
+        k = r.shape[0]
+        assert k <= hyp["max_predictions_per_img"]
+        if k == 0:
+            continue
+        seen += k
+        assert np.all(np.diff(r[:, 4]) <= 0)                                   # descending score
+        ties = np.diff(r[:, 4]) == 0
+        assert np.all(np.diff(idx[i])[ties] > 0)                               # equal scores: lower candidate first
+        d = decoded[i, torch.from_numpy(idx[i].astype(np.int64)).cuda()].cpu().numpy()
+        xyxy = np.stack([d[:, 0] - d[:, 2] / 2, d[:, 1] - d[:, 3] / 2, d[:, 0] + d[:, 2] / 2, d[:, 1] + d[:, 3] / 2], 1)
+        np.testing.assert_array_equal(r[:, :4], xyxy.astype(np.float32))
+        sc = d[:, 5:] * d[:, 4:5]
+        np.testing.assert_array_equal(r[:, 4], sc.max(1))
+        np.testing.assert_array_equal(r[:, 5], sc.argmax(1).astype(np.float32))
+        if i % 8 == 0:  # the pair tests below go through the array kernels; a sample of images keeps the test short
+            off = (r[:, :4] + r[:, 5:6] * np.float32(4096)).astype(np.float32)
+            iou = numba_iou(off, off)
+            np.fill_diagonal(iou, 0.0)
+            assert not (iou >= hyp["iou_threshold"]).any()                     # no kept pair the loop would have suppressed
+            assert numba_nms(off, r[:, 4].copy(), hyp["iou_threshold"]) == list(range(k))   # fixed point
+    assert seen > 0
+    # batch independence: image 5 alone gives the same rows
+    alone = pp.to_list(PostProcessor("yolov5", hyp, anchors=torch.tensor(synth.V5_ANCHORS_PX)).run(
+        [h[5:6].contiguous() for h in heads], 640, 640), as_numpy=True)[0]
+    assert (alone is None and rows[5] is None) or np.array_equal(alone, rows[5])
