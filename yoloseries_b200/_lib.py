@@ -7,7 +7,8 @@ import ctypes
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "_lib", "libysb_postproc.so")
+# YSB_LIBRARY: load another build of the same ABI (A/B runs of kernel experiments); default = the in-tree build
+LIB_PATH = os.environ.get("YSB_LIBRARY") or os.path.join(PKG, "_lib", "libysb_postproc.so")
 
 YSB_MAX_LEVELS = 8
 YSB_MAX_ANCHORS = 9
