@@ -25,7 +25,7 @@ if ROOT not in sys.path:
 
 METRIC = "post-proc images/s (YOLOv5s 640^2, conf=0.001)"
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
-NCU_TRAFFIC_BYTES = {("yolov5", 640, 64, "dense"): 524515456 + 8099072}  # mean of the two captured launches
+NCU_TRAFFIC_BYTES = {("yolov5", 640, 64, "dense"): 525095552 + 8164096}  # mean of the two captured launches
 UNIT = "images/s"
 
 
@@ -525,7 +525,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "host pinned head tensors -> ysb_filter_candidates + ysb_select_nms -> host rows/counts"},
             "gpu_launches": 2 * args.steps,
-            "roofline": {"kernel": ("k_filter_rows" if args.family in ("yolov7", "retinanet", "retinanet_exp") else "k_filter_planes<4>")
+            "roofline": {"kernel": ("k_filter_rows" if args.family in ("yolov7", "retinanet", "retinanet_exp") else "k_filter_planes_v4<9,128,6>" if args.family in ("yolov5", "yolox", "yolov8") else "k_filter_planes<4>")
                                    + " (decode-sigmoid + filter + class pick + compaction)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src,

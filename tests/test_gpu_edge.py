@@ -269,8 +269,9 @@ def test_cuda_graph_capture_replays_with_refilled_heads():
 
 
 def test_filter_kernel_variants_emit_the_same_survivors():
-    """The profiling variants of the filter kernel (cp.async ring, 1-D bulk-copy TMA ring, 2-D tensor-map TMA ring) are
-    selected by an environment variable read at library load: run each in a subprocess and compare survivor sets."""
+    """The default specialised kernel (every level 128-bit loadable), the generic kernel it replaces there, and the
+    profiling variants (tuning points, cp.async ring, 1-D bulk-copy TMA ring, 2-D tensor-map TMA ring) are selected by
+    environment variables read at library load: run each in a subprocess and compare survivor sets."""
     import os
     import subprocess
     import sys
@@ -293,7 +294,7 @@ for fam, img in (("yolov5", 320), ("yolox", 256), ("yolov8", 128)):
 '''
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = {}
-    for variant, ppt in (("1", "0"), ("3", "8"), ("3", "43"), ("2", "4"), ("0", "0")):
+    for variant, ppt in (("1", "0"), ("1", "50"), ("1", "37"), ("1", "41"), ("3", "8"), ("3", "43"), ("2", "4"), ("0", "0")):
         env = dict(os.environ, YSB_FILTER_VARIANT=variant, YSB_BULK_PPT=ppt)
         r = subprocess.run([sys.executable, "-c", child], cwd=root, env=env, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-1500:]

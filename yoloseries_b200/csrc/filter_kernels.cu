@@ -267,6 +267,104 @@ __global__ void __launch_bounds__(THREADS, MINB) k_filter_planes(const __grid_co
                    counts + img * 4, P.pre_kind == PRE_ANY_GT);
 }
 // -------------------------------------------------------------------------------------------------------
+// planes layout, every level 128-bit loadable (the common case: H*W % 4 == 0 on all levels, 16-byte aligned heads).
+// Same decomposition and results as k_filter_planes<4>; specialised so that
+//   * there is no per-level scalar fallback path (the generic kernel if-converts both paths and issues both),
+//   * plane addresses are 32-bit element offsets from the (image, anchor) block (2 integer ops per load instead of 6),
+//   * the last C % U class planes and the objectness plane are ONE batch of independent loads (the generic kernel walks
+//     the remainder one dependent load at a time and fetches objectness after the whole class scan).
+// -------------------------------------------------------------------------------------------------------
+template <int U, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_filter_planes_v4(const __grid_constant__ Plan P, uint64_t *__restrict__ keys,
+                                                                    int64_t key_cap, int32_t *__restrict__ counts)
+{
+    const int img = blockIdx.x;  // image-fastest grid: concurrent CTAs append to different per-image counters
+    const int u = blockIdx.y * THREADS + threadIdx.x;
+    const bool active = u < P.units_per_img;
+    uint64_t out[4] = {0ull, 0ull, 0ull, 0ull};
+    unsigned okm = 0u;
+    int npre = 0;
+    uint32_t smax_bits = 0u, smin_inv = 0u;
+    if (active) {
+        int l = 0;
+#pragma unroll
+        for (int i = 1; i < YSB_MAX_LEVELS; ++i)
+            if (i < P.L && u >= P.lv[i].unit_off) l = i;
+        const LevelDesc &lv = P.lv[l];
+        const uint32_t hw = static_cast<uint32_t>(lv.hw);
+        const int upa = lv.hw >> 2;  // units per anchor
+        const int ru = u - lv.unit_off;
+        const int a = ru / upa;
+        const int pos = (ru - a * upa) << 2;
+        const int cand0 = lv.cand_off + a * lv.hw + pos;
+        const float *cls = lv.p0 + (static_cast<size_t>(img * P.A + a) * P.cls_nch + P.cls_ch) * hw + pos;
+        const int C = P.C;
+
+        float m1[4], m2[4], objv[4];
+        int k0[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { m1[j] = -INFINITY; m2[j] = -INFINITY; k0[j] = 0; objv[j] = 0.0f; }
+
+        int k = 0;
+        uint32_t off = 0;  // k * hw, in elements: an (image, anchor) block is far below 2^32 floats
+        for (; k + U <= C; k += U, off += U * hw) {
+            float4 v[U];
+#pragma unroll
+            for (int q = 0; q < U; ++q) v[q] = ldg_stream4_256(cls + (off + q * hw));
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                top2_update(v[q].x, k + q, m1[0], m2[0], k0[0]);
+                top2_update(v[q].y, k + q, m1[1], m2[1], k0[1]);
+                top2_update(v[q].z, k + q, m1[2], m2[2], k0[2]);
+                top2_update(v[q].w, k + q, m1[3], m2[3], k0[3]);
+            }
+        }
+        {
+            // tail batch: the remaining (< U) class planes and the objectness plane, all in flight together
+            const int rem = C - k;
+            float4 v[U];
+            float4 ov = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (P.use_obj) {
+                const float *ob = (P.obj_src == 2 ? lv.p2 : lv.p0) +
+                                  (static_cast<size_t>(img * P.A + a) * P.obj_nch + P.obj_ch) * hw + pos;
+                ov = ldg_stream4_256(ob);
+            }
+#pragma unroll
+            for (int q = 0; q < U - 1; ++q)
+                if (q < rem) v[q] = ldg_stream4_256(cls + (off + q * hw));
+#pragma unroll
+            for (int q = 0; q < U - 1; ++q)
+                if (q < rem) {
+                    top2_update(v[q].x, k + q, m1[0], m2[0], k0[0]);
+                    top2_update(v[q].y, k + q, m1[1], m2[1], k0[1]);
+                    top2_update(v[q].z, k + q, m1[2], m2[2], k0[2]);
+                    top2_update(v[q].w, k + q, m1[3], m2[3], k0[3]);
+                }
+            objv[0] = ov.x; objv[1] = ov.y; objv[2] = ov.z; objv[3] = ov.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float score;
+            int c;
+            bool pre;
+            const float *cj = cls + j;
+            const bool ok = decide_candidate<false>(
+                P, m1[j], m2[j], k0[j], objv[j], [&](int kk) { return __ldg(cj + static_cast<size_t>(kk) * hw); }, score, c, pre);
+            npre += pre ? 1 : 0;
+            if (ok) {
+                out[j] = pack_key(score, static_cast<uint32_t>(P.cand_base + cand0 + j), static_cast<uint32_t>(c));
+                okm |= 1u << j;
+                const uint32_t sb = __float_as_uint(score);
+                smax_bits = max(smax_bits, sb);
+                smin_inv = max(smin_inv, ~sb);
+            }
+        }
+    }
+    emit_keys<4>(out, okm, npre, smax_bits, smin_inv, keys + static_cast<int64_t>(img) * key_cap, key_cap, counts + img * 4,
+                 P.pre_kind == PRE_ANY_GT);
+}
+
+// -------------------------------------------------------------------------------------------------------
 // planes layout, bulk-async version (the default when the heads are 16-byte aligned and H*W % 4 == 0).
 //
 // Persistent, warp-specialised: one CTA per SM = CW consumer warps + 1 producer warp.  A work item is 128*CW
@@ -1227,6 +1325,19 @@ cudaError_t launch_filter(const Plan &P, int vec, uint64_t *d_keys, int64_t key_
         const dim3 grid128 = img_fast ? dim3(P.batch, (P.units_per_img + 127) / 128) : dim3((P.units_per_img + 127) / 128, P.batch);
         if (vec == 1) {
             k_filter_planes<1><<<grid, 256, 0, stream>>>(P, d_keys, key_cap, d_counts);
+        } else if (vec == 4 && (g_bulk_ppt == 0 || (g_bulk_ppt >= 30 && g_bulk_ppt <= 45))) {
+            // every level 128-bit loadable (the common case): specialised kernel; g_bulk_ppt 30..45 = its tuning variants
+            const dim3 gv4(P.batch, (P.units_per_img + 127) / 128);
+            switch (g_bulk_ppt) {
+            case 31: k_filter_planes_v4<16, 128, 4><<<gv4, 128, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
+            case 33: k_filter_planes_v4<9, 128, 6><<<gv4, 128, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
+            case 37: k_filter_planes_v4<6, 128, 8><<<gv4, 128, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
+            case 41: k_filter_planes_v4<9, 64, 12><<<dim3(P.batch, (P.units_per_img + 63) / 64), 64, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
+            case 30: k_filter_planes_v4<12, 128, 5><<<gv4, 128, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
+            // default: 9 loads of 128 bits in flight per thread (YOLOv5/YOLOX: 80 classes + objectness = 9 batches of 9),
+            // 76 registers, 6 CTAs of 128 threads per SM
+            default: k_filter_planes_v4<9, 128, 6><<<gv4, 128, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
+            }
         } else {
             switch (g_bulk_ppt) {  // profiling variants of the direct-load kernel
             case 3: k_filter_planes<4, 4, 256, 6><<<grid, 256, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
@@ -1243,8 +1354,8 @@ cudaError_t launch_filter(const Plan &P, int vec, uint64_t *d_keys, int64_t key_
             case 21: k_filter_planes<4, 8, 256, 4, 1><<<grid, 256, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
             case 22: k_filter_planes<4, 8, 128, 8, 1><<<grid128, 128, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
             case 24: k_filter_planes<4, 16, 128, 4, 1><<<grid128, 128, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
-            // default: 128-thread CTAs, 12 loads of 128 bits in flight per thread (96 registers, 5 CTAs/SM), 256-byte L2
-            // prefetch granularity
+            // generic kernel (levels that are not all 128-bit loadable, e.g. FCOS' 5x5 map; YSB_BULK_PPT=50 forces it):
+            // 128-thread CTAs, 12 loads of 128 bits in flight per thread (96 registers, 5 CTAs/SM), 256-byte L2 prefetch
             default: k_filter_planes<4, 12, 128, 5, 1><<<grid128, 128, 0, stream>>>(P, d_keys, key_cap, d_counts); break;
             }
         }
