@@ -463,6 +463,13 @@ def run_ours(args):
     torch.cuda.synchronize()
     iso_ms = statistics.mean(a.elapsed_time(b_) for a, b_ in iso)
     m_mean = float(slots[0].counts[:, 0].float().mean().item())
+    # every rank's own speed on the HBM-bound kernel: the collectives make all ranks run at the slowest one's pace
+    iso_per_rank = [iso_ms]
+    if world > 1:
+        tt = torch.tensor([iso_ms], dtype=torch.float64, device=dev)
+        allv = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allv, tt)
+        iso_per_rank = [float(x) for x in allv.tolist()]
 
     # ---- end-to-end: host (pinned) heads -> H2D -> kernels -> D2H of rows + counts, per step -------------------
     host_heads = [torch.empty(t_.shape, dtype=t_.dtype, pin_memory=True).copy_(t_) for t_ in flat]
@@ -525,6 +532,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "host pinned head tensors -> ysb_filter_candidates + ysb_select_nms -> host rows/counts"},
             "gpu_launches": 2 * args.steps,
+            "filter_alone_ms_per_rank": [round(x, 5) for x in iso_per_rank],
             "roofline": {"kernel": ("k_filter_rows" if args.family in ("yolov7", "retinanet", "retinanet_exp") else "k_filter_planes_v4<9,128,6>" if args.family in ("yolov5", "yolox", "yolov8") else "k_filter_planes<4>")
                                    + " (decode-sigmoid + filter + class pick + compaction)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
