@@ -4,9 +4,14 @@ import oracle
 from yoloseries_b200 import synth, _lib
 from yoloseries_b200.engine import PostProcessor
 lib = _lib.load()
-for dist in ("dense", "sparse", "crowd"):
-    heads = synth.make_heads("yolov5", 64, 640, 640, 80, dist, 1234, "cuda")
-    pp = PostProcessor("yolov5", oracle.default_hyp(), anchors=torch.tensor(synth.V5_ANCHORS_PX))
+fam = sys.argv[1] if len(sys.argv) > 1 else "yolov5"
+dists = ("dense", "sparse", "crowd") if fam == "yolov5" else ("dense", "sparse")
+for dist in dists:
+    heads = synth.make_heads(fam, 64, 640, 640, 80, dist, 1234, "cuda")
+    hyp = oracle.default_hyp()
+    if fam == "fcos":
+        hyp.update(cls_threshold=0.2, iou_threshold=0.35, max_predictions_per_img=100)
+    pp = PostProcessor(fam, hyp, anchors=torch.tensor(synth.V5_ANCHORS_PX) if fam in ("yolov5", "yolov7") else None)
     for _ in range(3):
         pp.run(heads, 640, 640)
     torch.cuda.synchronize()

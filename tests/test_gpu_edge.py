@@ -303,3 +303,29 @@ for fam, img in (("yolov5", 320), ("yolox", 256), ("yolov8", 128)):
     assert len(base) == 3 and all(int(line.split()[1]) > 0 for line in base)
     for k, v in outs.items():
         assert v == base, (k, v, base)
+
+
+def test_boxes_wider_than_the_class_offset():
+    """The reference separates classes by adding cls * 4096 to the boxes (eval_yolov5.py:293-297), which only works while
+    boxes stay inside [0, 4096]: wider or negative boxes of DIFFERENT classes do overlap in its arithmetic, in the NMS
+    and in the postprocess_bbox count.  The class-bucketed count filter must notice and fall back to all pairs."""
+    rng = np.random.default_rng(5)
+    n, C = 600, 6
+    hyp = oracle.default_hyp(num_class=C, conf_threshold=0.0, cls_threshold=0.0, iou_threshold=0.3)
+    for widen in (False, True):
+        dec = np.zeros((2, n, 5 + C), dtype=np.float32)
+        dec[..., 0:2] = rng.uniform(100, 500, size=(2, n, 2))
+        dec[..., 2:4] = rng.uniform(20, 120, size=(2, n, 2))
+        if widen:  # a few boxes several class offsets wide and some with negative x1: cross-class overlaps exist
+            dec[:, :40, 2] = rng.uniform(3000, 15000, size=(2, 40))
+            dec[:, 40:60, 0] = rng.uniform(-300, 10, size=(2, 20))
+        dec[..., 4] = rng.uniform(0.3, 1.0, size=(2, n))
+        dec[..., 5:] = rng.uniform(0.0, 1.0, size=(2, n, C))
+        want = oracle.evaluator_nms("yolov5", dec, hyp)
+        pp = _pp("yolov5", hyp)
+        rows, idx = pp.to_list(pp.run(torch.from_numpy(dec).cuda(), 640, 640, decoded=True), as_numpy=True, with_index=True)
+        for i, w in enumerate(want):
+            assert (w.rows is None) == (rows[i] is None)
+            if w.rows is not None:
+                np.testing.assert_array_equal(rows[i], w.rows)
+                np.testing.assert_array_equal(idx[i], w.cand_index)

@@ -226,6 +226,14 @@ __device__ void bitonic_sort_desc(uint64_t *keys, int n)
     __syncthreads();
 }
 
+// order-preserving float <-> int maps (signed integer compare == float compare; used for shared-memory atomicMin/Max)
+__device__ __forceinline__ int float_ordered(float f)
+{
+    const int i = __float_as_int(f);
+    return i ^ ((i >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float ordered_float(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+
 // Plan a merged candidate index belongs to (test-time-augmentation passes); cand becomes the index inside that pass.
 __device__ __forceinline__ const Plan &pass_of(const Plan &P, const NoExtraPasses &, int &) { return P; }
 __device__ __forceinline__ const Plan &pass_of(const Plan &P, const ExtraPasses &X, int &cand)
@@ -323,25 +331,49 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
             const int cn = min(kChunk, n_use - c0);
             K2_ACC_BEGIN();
             if (c0 + cn > decoded_upto) {
-                if (!ARRAY && P.family == YSB_YOLOV8 && P.input_kind == YSB_INPUT_RAW_HEADS) {
-                    // the DFL decode is 64 loads + 32 exp per box: four threads per candidate (one per side), 256 per round
-                    const int i = decoded_upto + (tid >> 2), side = tid & 3;
-                    float sv = 0.0f;
-                    int cand = 0;
-                    if (i < n_use) {
-                        cand = static_cast<int>(key_cand(S.keys[i]));
-                        const Plan &Q = pass_of(P, X, cand);
-                        sv = v8_side_value(Q, img, cand, side);
+                if (!ARRAY && P.family == YSB_YOLOV8 && P.input_kind == YSB_INPUT_RAW_HEADS && P.dfl_bins <= 16) {
+                    // DFL decode of exactly this chunk.  A box needs 4 sides x 16 bins = 64 scattered loads: (i) sixteen
+                    // threads per candidate fetch 4 bin logits each (all independent, one round trip) into shared memory
+                    // laid out [bin][candidate*4 + side]; (ii) one thread per (candidate, side) runs the softmax
+                    // expectation from shared memory (conflict-free: consecutive threads, consecutive words) in the
+                    // same bin order as the decode kernel; (iii) the four sides of a candidate meet by shuffle.
+                    float *dfl = S.area;  // 16 x 256 floats; the areas are only used by the post-filter, after this loop
+                    {
+                        const int j = tid >> 4, part = tid & 15, side = part >> 2, b0 = (part & 3) << 2;
+                        if (j < cn) {
+                            int cand = static_cast<int>(key_cand(S.keys[c0 + j]));
+                            const Plan &Q = pass_of(P, X, cand);
+                            const LevelDesc &lv = Q.lv[find_level(Q, cand)];
+                            const float *q = lv.p0 + (static_cast<size_t>(img) * Q.cls_nch + static_cast<size_t>(side) * Q.dfl_bins) * lv.hw +
+                                             (cand - lv.cand_off);
+                            float v[4];
+#pragma unroll
+                            for (int b = 0; b < 4; ++b)
+                                v[b] = (b0 + b) < Q.dfl_bins ? __ldg(q + static_cast<size_t>(b0 + b) * lv.hw) : -INFINITY;
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) dfl[(b0 + b) * 256 + j * 4 + side] = v[b];
+                        }
                     }
-                    const unsigned qb = (tid & 31) & ~3u;
-                    const float s0 = __shfl_sync(0xffffffffu, sv, qb), s1 = __shfl_sync(0xffffffffu, sv, qb + 1);
-                    const float s2 = __shfl_sync(0xffffffffu, sv, qb + 2), s3 = __shfl_sync(0xffffffffu, sv, qb + 3);
-                    if (side == 0 && i < n_use) {
-                        int full = static_cast<int>(key_cand(S.keys[i]));
-                        const Plan &Q = pass_of(P, X, full);
-                        S.raw[i] = tta_undo(Q, v8_box_from_sides(Q, full, s0, s1, s2, s3));
+                    __syncthreads();
+                    if (tid < 256) {
+                        const int j = tid >> 2, side = tid & 3;
+                        float sv = 0.0f;
+                        if (j < cn) {
+                            float v[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = dfl[i * 256 + tid];
+                            sv = v8_side_from_bins(v, P.dfl_bins);
+                        }
+                        const unsigned qb = (tid & 31) & ~3u;
+                        const float s0 = __shfl_sync(0xffffffffu, sv, qb), s1 = __shfl_sync(0xffffffffu, sv, qb + 1);
+                        const float s2 = __shfl_sync(0xffffffffu, sv, qb + 2), s3 = __shfl_sync(0xffffffffu, sv, qb + 3);
+                        if (side == 0 && j < cn) {
+                            int cand = static_cast<int>(key_cand(S.keys[c0 + j]));
+                            const Plan &Q = pass_of(P, X, cand);
+                            S.raw[c0 + j] = tta_undo(Q, v8_box_from_sides(Q, cand, s0, s1, s2, s3));
+                        }
                     }
-                    decoded_upto = min(n_use, decoded_upto + kThreads / 4);
+                    decoded_upto = c0 + cn;
                 } else {
                     const int i = decoded_upto + tid;
                     if (i < n_use) {
@@ -485,15 +517,87 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
         const int warp = tid >> 5, lane = tid & 31;
         const int mm = min(n_tranche, limit);
         if (!P.merge_boxes) {
-            // offset boxes + areas once per survivor (in place: the raw boxes of the kept rows live in kept_raw)
+            // offset boxes + areas once per survivor (in place: the raw boxes of the kept rows live in kept_raw).
+            // The 4096-px class offset keeps boxes of different classes disjoint in x as long as the raw boxes span at
+            // most 4095 px: for classes a < b, fl(x2 + 4096 a) - fl(x1' + 4096 b) <= (max x2 - min x1) - 4096 + 0.5 < 0
+            // (offset values stay below 2^23, so each rounding moves them by at most 0.25).  Then a kept box only needs
+            // the survivors of its own class: bucket the survivors by class (counting sort of their indices in shared
+            // memory) and walk one bucket per kept box instead of all M survivors.  Otherwise (huge boxes -- the
+            // reference then lets classes interact) every pair is tested.
+            int lo_x = 0x7fffffff, hi_x = static_cast<int>(0x80000000u);
+            bool finite = true;
             for (int j = tid; j < mm; j += kThreads) {
                 const uint64_t key = S.keys[j];
                 const float off = P.class_aware ? __fmul_rn(static_cast<float>(key_cls(key)), 4096.0f) : 0.0f;
-                const OffBox b = make_offbox(S.raw[j], off);
+                const float4 rb = S.raw[j];
+                finite = finite && (fabsf(rb.x) <= 3.0e38f) && (fabsf(rb.z) <= 3.0e38f);  // false for NaN / inf
+                lo_x = min(lo_x, float_ordered(rb.x));
+                hi_x = max(hi_x, float_ordered(rb.z));
+                const OffBox b = make_offbox(rb, off);
                 S.raw[j] = make_float4(b.x1, b.y1, b.x2, b.y2);
                 S.area[j] = b.area;
             }
+            lo_x = __reduce_min_sync(0xffffffffu, lo_x);
+            hi_x = __reduce_max_sync(0xffffffffu, hi_x);
+            if (tid == 0) { S.sel_digit = 0x7fffffff; S.sel_above = static_cast<int>(0x80000000u); }
+            const bool all_finite = __syncthreads_and(finite ? 1 : 0);
+            if (lane == 0) { atomicMin(&S.sel_digit, lo_x); atomicMax(&S.sel_above, hi_x); }
             __syncthreads();
+            const float span = __fsub_rn(ordered_float(S.sel_above), ordered_float(S.sel_digit));
+            const bool buckets = P.class_aware && thr.positive && P.C <= kThreads && all_finite && span <= 4095.0f;
+            if (buckets) {
+                uint32_t *cnt_cls = S.hist;                 // [0, C]: bucket starts; [kThreads, kThreads + C): fill cursors
+                uint16_t *order = reinterpret_cast<uint16_t *>(S.raw + 3072);  // mm < 3000: the tail of raw[] is free
+                cnt_cls[tid] = 0;
+                __syncthreads();
+                for (int j = tid; j < mm; j += kThreads) atomicAdd(&cnt_cls[key_cls(S.keys[j])], 1u);
+                __syncthreads();
+                // exclusive scan over the classes (one per thread)
+                const uint32_t mine = cnt_cls[tid];
+                uint32_t incl = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                if (lane == 31) S.warp_tmp[warp] = incl;
+                __syncthreads();
+                if (warp == 0) {
+                    uint32_t w = S.warp_tmp[lane];
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t v = __shfl_up_sync(0xffffffffu, w, d);
+                        if (lane >= d) w += v;
+                    }
+                    S.warp_tmp[lane] = w;  // inclusive over warps
+                }
+                __syncthreads();
+                const uint32_t start = incl - mine + (warp > 0 ? S.warp_tmp[warp - 1] : 0u);
+                cnt_cls[tid] = start;
+                S.hist[kThreads + tid] = start;
+                __syncthreads();
+                for (int j = tid; j < mm; j += kThreads) {
+                    const uint32_t at = atomicAdd(&S.hist[kThreads + key_cls(S.keys[j])], 1u);
+                    order[at] = static_cast<uint16_t>(j);
+                }
+                __syncthreads();
+                for (int r = warp; r < kept; r += kThreads / 32) {
+                    const OffBox br = soa_load(kept_box, r);
+                    const uint32_t cls_r = key_cls(S.kept_key[r]);
+                    const int lo = static_cast<int>(cnt_cls[cls_r]), hi = static_cast<int>(S.hist[kThreads + cls_r]);
+                    int c = 0;
+                    for (int q = lo + lane; q < hi; q += 32) {
+                        const int j = order[q];
+                        const float4 o = S.raw[j];
+                        const float dw = __fsub_rn(fminf(br.x2, o.z), fmaxf(br.x1, o.x));
+                        const float dh = __fsub_rn(fminf(br.y2, o.w), fmaxf(br.y1, o.y));
+                        if (!(dw > 0.0f && dh > 0.0f)) continue;
+                        c += iou_decide<true>(dw, dh, br.area, S.area[j], thr) ? 1 : 0;
+                    }
+                    c = __reduce_add_sync(0xffffffffu, c);
+                    if (lane == 0) S.kept_flag[r] = c > 1;
+                }
+            } else {
             for (int r = warp; r < kept; r += kThreads / 32) {
                 const OffBox br = soa_load(kept_box, r);
                 int c = 0;
@@ -506,6 +610,7 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
                 }
                 c = __reduce_add_sync(0xffffffffu, c);
                 if (lane == 0) S.kept_flag[r] = c > 1;
+            }
             }
         } else {
         for (int r = warp; r < kept; r += kThreads / 32) {
