@@ -1110,11 +1110,33 @@ __global__ void __launch_bounds__(kRowsTile) k_filter_rows(const __grid_constant
         // thread t reads word sstride*t + k: conflict-free when sstride is odd; otherwise start the walk at column t so
         // that the 32 lanes hit (sstride+1)*t + k.  The visiting order is irrelevant: a unique maximum has a unique
         // index, and equal maxima force m2 == m1, i.e. the literal path, which walks in index order.
-        int k = (sstride & 1) ? 0 : static_cast<int>(threadIdx.x) % P.C;
+        if (sstride & 1) {
+            // odd stride (YOLOv7's 85-float rows): already conflict-free, a straight run without the wrap test
 #pragma unroll 8
-        for (int t = 0; t < P.C; ++t) {
-            top2_update(cls[k], k, m1, m2, k0);
-            if (++k == P.C) k = 0;
+            for (int k = 0; k < P.C; ++k) top2_update(cls[k], k, m1, m2, k0);
+        } else {
+            // rotated walk: lane l starts at column l, i.e. reads word sstride*tid + l + t = (sstride + 1)*l + t (mod 32)
+            // -- an odd multiplier, conflict-free.  Every lane runs the same C iterations (two straight runs per lane
+            // would diverge); the first C - 32 of them cannot wrap, so only the last 32 carry the wrap test.
+            const int lane = static_cast<int>(threadIdx.x) & 31;
+            if (P.C >= 32) {
+                const int straight = P.C - 32;
+#pragma unroll 8
+                for (int t = 0; t < straight; ++t) top2_update(cls[t + lane], t + lane, m1, m2, k0);
+                int k = straight + lane;
+#pragma unroll 8
+                for (int t = 0; t < 32; ++t) {
+                    if (k >= P.C) k -= P.C;
+                    top2_update(cls[k], k, m1, m2, k0);
+                    ++k;
+                }
+            } else {
+                int k = lane % P.C;
+                for (int t = 0; t < P.C; ++t) {
+                    top2_update(cls[k], k, m1, m2, k0);
+                    if (++k == P.C) k = 0;
+                }
+            }
         }
         const int cand = lv.cand_off + r0 + threadIdx.x;
         float objv = 0.0f;
