@@ -13,6 +13,14 @@
 //
 // Output: one 64-bit sort key per survivor, written with warp-aggregated atomics (order inside an image is
 // irrelevant: the key carries the candidate index, see pack_key).
+//
+// Kernels in this file (dispatch: launch_filter at the bottom):
+//   k_filter_planes_v4     NCHW heads whose levels are all 128-bit loadable (YOLOv5 / YOLOX / YOLOv8)   -- product path
+//   k_filter_planes        NCHW heads with levels that are not (FCOS' 5x5 map); generic                   -- product path
+//   k_filter_rows          channels-last heads and the decoded (b, N, C') tensor (YOLOv7, RetinaNet)      -- product path
+//   k_filter_multilabel    hyp['mutil_label']: one key per (candidate, class)                              -- product path
+//   k_filter_planes_async / _bulk / _tma   cp.async ring, 1-D bulk-copy TMA ring, 2-D tensor-map TMA ring  -- profiling
+//       variants selected by YSB_FILTER_VARIANT (same survivor sets, slower on this access pattern; profiles/README.md)
 #include <cuda.h>
 
 #include <cstdlib>
