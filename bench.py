@@ -61,8 +61,8 @@ def workload_config(args, world):
 
 
 def bench_hyp(family="yolov5"):
-    import oracle
-    hyp = oracle.default_hyp(num_class=80)
+    from yoloseries_b200 import synth
+    hyp = synth.map_profile_hyp(num_class=80)
     if family == "fcos":  # config/train_fcos.yaml:110-116
         hyp.update(cls_threshold=0.2, iou_threshold=0.35, max_predictions_per_img=100)
     return hyp

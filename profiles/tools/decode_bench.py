@@ -2,7 +2,6 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
-import oracle
 from yoloseries_b200 import synth
 from yoloseries_b200.engine import PostProcessor
 
@@ -10,7 +9,7 @@ for family, img, batch in (("yolov5", 640, 64), ("yolov7", 640, 64), ("yolox", 6
                            ("retinanet", 640, 32), ("fcos", 640, 128)):
     heads = synth.make_heads(family, batch, img, img, 80, "dense", 1, "cuda")
     anchors = torch.tensor(synth.V5_ANCHORS_PX) if family in ("yolov5", "yolov7") else None
-    pp = PostProcessor(family, oracle.default_hyp(), anchors=anchors)
+    pp = PostProcessor(family, synth.map_profile_hyp(), anchors=anchors)
     for _ in range(3):
         out = pp.decode(heads, img, img)
     torch.cuda.synchronize()

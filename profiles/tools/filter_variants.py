@@ -9,11 +9,10 @@ import sys
 CHILD = r'''
 import hashlib, sys, torch
 sys.path.insert(0, ".")
-import oracle
 from yoloseries_b200 import synth
 from yoloseries_b200.engine import PostProcessor
 fam, batch = sys.argv[1], int(sys.argv[2])
-hyp = oracle.default_hyp(num_class=80)
+hyp = synth.map_profile_hyp(num_class=80)
 anchors = torch.tensor(synth.V5_ANCHORS_PX) if fam in ("yolov5", "yolov7") else None
 pp = PostProcessor(fam, hyp, anchors=anchors)
 sets = [synth.make_heads(fam, batch, 640, 640, 80, "dense", seed=40 + k, device="cuda") for k in range(3)]

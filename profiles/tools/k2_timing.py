@@ -1,6 +1,5 @@
 import ctypes, sys, torch, numpy as np
 sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))))
-import oracle
 from yoloseries_b200 import synth, _lib
 from yoloseries_b200.engine import PostProcessor
 lib = _lib.load()
@@ -8,7 +7,7 @@ fam = sys.argv[1] if len(sys.argv) > 1 else "yolov5"
 dists = ("dense", "sparse", "crowd") if fam == "yolov5" else ("dense", "sparse")
 for dist in dists:
     heads = synth.make_heads(fam, 64, 640, 640, 80, dist, 1234, "cuda")
-    hyp = oracle.default_hyp()
+    hyp = synth.map_profile_hyp()
     if fam == "fcos":
         hyp.update(cls_threshold=0.2, iou_threshold=0.35, max_predictions_per_img=100)
     pp = PostProcessor(fam, hyp, anchors=torch.tensor(synth.V5_ANCHORS_PX) if fam in ("yolov5", "yolov7") else None)

@@ -6,7 +6,6 @@ import numpy as np
 import torch
 
 sys.path.insert(0, ".")
-import oracle  # noqa: E402  (hyp defaults only)
 from yoloseries_b200 import synth  # noqa: E402
 from yoloseries_b200.engine import PostProcessor, preds_postprocess  # noqa: E402
 from yoloseries_b200.utils import (gpu_CIoU, gpu_DIoU, gpu_Giou, gpu_exponential_soft_nms, gpu_iou,  # noqa: E402
@@ -15,7 +14,7 @@ from yoloseries_b200.utils import (gpu_CIoU, gpu_DIoU, gpu_Giou, gpu_exponential
 C = 8
 for fam, img in (("yolov5", 128), ("yolov7", 128), ("yolox", 96), ("yolov8", 64), ("retinanet", 64), ("retinanet_exp", 64),
                  ("fcos", 160)):
-    hyp = oracle.default_hyp(num_class=C)
+    hyp = synth.map_profile_hyp(num_class=C)
     if fam == "fcos":
         hyp.update(cls_threshold=0.2, iou_threshold=0.35, max_predictions_per_img=100)
     anchors = torch.tensor(synth.V5_ANCHORS_PX) if fam in ("yolov5", "yolov7") else None

@@ -6,12 +6,11 @@ import sys
 import torch
 
 sys.path.insert(0, ".")
-import oracle  # noqa: E402  (default_hyp only)
 from yoloseries_b200 import synth  # noqa: E402
 from yoloseries_b200.engine import PostProcessor  # noqa: E402
 
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-hyp = oracle.default_hyp(num_class=80)
+hyp = synth.map_profile_hyp(num_class=80)
 pp = PostProcessor("yolov5", hyp, anchors=torch.tensor(synth.V5_ANCHORS_PX))
 S, Fl = (1, 0.83, 0.67), (None, 2, 3)
 passes = [(synth.make_heads("yolov5", batch, 640, 640, 80, "dense", seed=10 + k, device="cuda"), 640, 640, s, f)

@@ -169,3 +169,15 @@ def _crowd_v5(batch, shapes, C, g, device, objects_per_image=700):
                         tgt[5:, yy, xx] = _randn((C, n), g, device, mean=-4.0, std=1.0)
                         tgt[5 + cls_id[idx], yy, xx] = _randn((n,), g, device, mean=2.5, std=1.0)
     return [t.view(batch, 3 * (5 + C), t.shape[3], t.shape[4]).contiguous() for t in heads]
+
+
+def map_profile_hyp(**over):
+    """The reference's mAP-profile post-processing settings (config/train_yolov5.yaml:85-111 'compute_metric_*',
+    config/validation.yaml:3-20) as the flat ``hyp`` dict engine.make_params reads; ``over`` replaces entries."""
+    hyp = dict(
+        num_class=80, conf_threshold=0.001, cls_threshold=0.001, iou_threshold=0.65, max_predictions_per_img=300,
+        min_prediction_box_wh=2, mutil_label=False, agnostic=True, postprocess_bbox=True, pre_nms_topk=1000,
+        pre_nms_thresh=0.05, thresh_with_ctr=True,
+    )
+    hyp.update(over)
+    return hyp
