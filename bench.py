@@ -245,6 +245,15 @@ def run_ours(args):
 
     from yoloseries_b200 import _lib, synth
     from yoloseries_b200.engine import PostProcessor, flatten_heads
+    if not os.path.exists(_lib.LIB_PATH):  # fresh checkout: the built library is git-ignored
+        if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+            from yoloseries_b200 import build as ysb_build
+            print("bench.py: libysb_postproc.so missing, building it with nvcc ...", file=sys.stderr)
+            ysb_build.build()
+        else:  # the other ranks wait for rank 0's build (the link is renamed into place atomically)
+            deadline = time.time() + 900
+            while not os.path.exists(_lib.LIB_PATH) and time.time() < deadline:
+                time.sleep(1.0)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

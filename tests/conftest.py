@@ -17,6 +17,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """The in-tree libysb_postproc.so normally travels with the snapshot; a fresh checkout (the .so is git-ignored)
+    gets it built once per session.  Building is not a fallback: without nvcc this raises and every test fails loudly."""
+    from yoloseries_b200 import _lib, build
+    if not os.path.exists(_lib.LIB_PATH) and not os.environ.get("YSB_LIBRARY"):
+        build.build()
+    yield
+
+
 def pytest_collection_modifyitems(config, items):
     try:
         import torch
