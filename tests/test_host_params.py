@@ -82,3 +82,20 @@ def test_letterbox_table_and_argument_errors():
         engine.make_params("yolox", oracle.default_hyp(), 1, 64, 64, None)                  # level shapes required
     with pytest.raises(ValueError):
         engine.preds_postprocess([None], [])
+
+
+def test_normalise_heads_is_a_no_op_for_reference_outputs_and_fixes_the_rest():
+    from collections import OrderedDict
+    a = torch.zeros(2, 255, 8, 8)
+    assert engine.normalise_heads(a) is a                                    # float32 + contiguous: untouched, no copy
+    lst = [a, torch.zeros(2, 255, 4, 4)]
+    out = engine.normalise_heads(lst)
+    assert isinstance(out, list) and out[0] is a and out[1] is lst[1]
+    half = torch.zeros(2, 3, 8, 8, 85, dtype=torch.float16)
+    view = torch.zeros(2, 85, 3, 8, 8).permute(0, 2, 3, 4, 1)                # channels-last view, not contiguous
+    d = engine.normalise_heads(OrderedDict(p0=half, p1=view))
+    assert isinstance(d, OrderedDict) and list(d) == ["p0", "p1"]
+    assert d["p0"].dtype == torch.float32 and d["p1"].is_contiguous() and d["p1"].shape == view.shape
+    fcos = ([a], [torch.zeros(2, 4, 8, 8)], [torch.zeros(2, 1, 8, 8).half()])
+    f = engine.normalise_heads(fcos)
+    assert isinstance(f, tuple) and f[0][0] is a and f[2][0].dtype == torch.float32

@@ -51,6 +51,19 @@ def flatten_heads(family, heads):
     return list(heads)
 
 
+def normalise_heads(heads):
+    """Model outputs as the engine needs them: float32 and contiguous, same nesting.  A no-op (no copy) for what the
+    reference's models emit by default; half-precision or permuted-view outputs are converted like the reference's own
+    ``.float()`` / ``.contiguous()`` calls (trainer/eval_yolov5.py:194, 265)."""
+    if isinstance(heads, torch.Tensor):
+        if heads.dtype == torch.float32 and heads.is_contiguous():
+            return heads
+        return heads.detach().to(torch.float32).contiguous()
+    if isinstance(heads, (dict, OrderedDict)):
+        return type(heads)((k, normalise_heads(v)) for k, v in heads.items())
+    return type(heads)(normalise_heads(v) for v in heads)
+
+
 def _level_shapes(family, flat, num_class):
     if family in ("yolov5", "yolox", "yolov8"):
         return [(t.shape[-2], t.shape[-1]) for t in flat]

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from ..engine import PostProcessor
+from ..engine import PostProcessor, normalise_heads
 
 __all__ = ["YOLOV5Evaluator", "YOLOV7Evaluator", "YOLOXEvaluator", "YOLOV8Evaluator", "RetinaNetEvaluator",
            "RetinaNetEvaluatorExperiment", "FCOSEvaluator"]
@@ -49,14 +49,14 @@ class _Evaluator:
             # three model forwards, then ONE fused call: no decoded or merged tensor is written (ysb_postprocess_tta)
             out = self._pp.run_tta(self._tta_passes(inputs), (inputs.size(2), inputs.size(3)))
             return self._pp.to_list(out)
-        heads = self._model(inputs)
+        heads = normalise_heads(self._model(inputs))
         out = self._pp.run(heads, inputs.size(2), inputs.size(3))
         return self._pp.to_list(out)
 
     @torch.no_grad()
     def do_inference(self, inputs):
         """model forward + decode -> (b, N, C') float32 on the heads' device (one CUDA kernel, ysb_decode)."""
-        heads = self._model(inputs)
+        heads = normalise_heads(self._model(inputs))
         return self._pp.decode(heads, inputs.size(2), inputs.size(3))
 
     def numba_nms(self, preds_out):
@@ -84,7 +84,7 @@ class _Evaluator:
         for s, f in zip([1, 0.83, 0.67], [None, 2, 3]):
             img = inputs.flip(dims=(f,)) if f else inputs
             img = self.scale_img(img, s)
-            passes.append((self._model(img), img.size(2), img.size(3), s, f))
+            passes.append((normalise_heads(self._model(img)), img.size(2), img.size(3), s, f))
         return passes
 
     def test_time_augmentation(self, inputs):
