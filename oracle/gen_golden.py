@@ -257,6 +257,11 @@ def main():
         ("yolox_multilabel", "yolox", "dense", 64, 2, 74, 4, {"mutil_label": True, "compute_metric_cls_threshold": 0.3}),
         ("yolov8_multilabel", "yolov8", "dense", 64, 1, 75, 4, {"mutil_label": True, "compute_metric_cls_threshold": 0.5}),
         ("fcos_multilabel", "fcos", "dense", 128, 1, 76, 4, dict(fcos_thr, mutil_label=True)),
+        # cpu_*: pinned on the oracle side only so far (not yet part of the GPU parametrisations, see tests/conftest.py)
+        ("cpu_fcos_no_ctr", "fcos", "dense", 128, 2, 91, 4, dict(fcos_thr, thresh_with_ctr=False)),
+        ("cpu_retinanet_exp_sparse", "retinanet_exp", "sparse", 96, 2, 92, 6, {}),
+        ("cpu_yolov5_agnostic_off_multilabel", "yolov5", "crowd", 128, 1, 93, 6,
+         {"agnostic": False, "mutil_label": True, "compute_metric_cls_threshold": 0.05}),
     ]
     only = set(sys.argv[1:])
     tta_cases = [

@@ -26,7 +26,7 @@ def _decode(family, heads, meta):
     raise ValueError(family)
 
 
-@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("name", golden_names() + golden_names("cpu_"))
 def test_decode_matches_reference(name):
     g = load_golden(name)
     fam = g["meta"]["family"]
@@ -48,7 +48,7 @@ def test_decode_matches_reference(name):
         assert ok.all(), f"max abs err {np.abs(got - ref).max()}"
 
 
-@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("name", golden_names() + golden_names("cpu_"))
 def test_evaluator_nms_matches_reference(name):
     g = load_golden(name)
     fam = g["meta"]["family"]
@@ -69,7 +69,7 @@ def test_evaluator_nms_matches_reference(name):
             np.testing.assert_array_equal(r.rows, ref)
 
 
-@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("name", golden_names() + golden_names("cpu_"))
 def test_early_stop_equals_full(name):
     g = load_golden(name)
     fam = g["meta"]["family"]
