@@ -1,20 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- post-processing throughput (images/s) of the B200 engine on BASELINE.json's headline config.
+"""bench.py -- post-processing throughput (images/s) of the B200 engine on BASELINE.json's configs.
 
   python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
-  python bench.py --impl reference --gpus N --steps K ...  (the reference's CPU algorithm on the host cores)
+  python bench.py --impl reference --gpus N --steps K ...  (the UNMODIFIED reference on the host cores)
+  python bench.py --config c3|c4|c5 ...                    (the other BASELINE configs; c2 is the default / headline)
 
-A "step" is one pass of the hot path (filter/compaction kernel + select/sort/NMS kernel) over one batch of
-synthetic YOLOv5s 640x640 head tensors (3 levels, 25,200 candidates/image, 80 classes, conf=cls=0.001, iou=0.65,
-max_det=300, class-aware).  Every rank owns `--batch` images (weak scaling: BASELINE config[1]'s 64 images per
-GPU); at N > 1 the step ends with the all-gather of the padded kept detections (the only collective on the path).
+A "step" is one pass of the hot path (decode-score + filter + compaction kernel, select + sort + class-aware NMS +
+post-filter kernel) over one batch of synthetic head tensors, through yoloseries_b200.dist.ShardedPostProcessor -- the
+package's own multi-GPU API: every rank owns `batch` images per step (weak scaling), several batches in flight on
+separate CUDA streams, and at N > 1 the NMS kernel stores the kept rows straight into every peer's receive slot over
+NVLink (no collective launch).  Headline (c2): YOLOv5s 640x640, 3 levels, 25 200 candidates/image, 80 classes,
+conf = cls = 0.001, iou = 0.65, max_det = 300, class-aware, 64 images per GPU per step.
 
-Output: ONE JSON line on rank 0 (see the keys in main()).
+Output: ONE JSON line on rank 0.  Besides the contract keys it carries `distributions` (the same shape on sparse and
+crowd inputs), `c2_strong` (BASELINE's "batch 64 sharded over N GPUs" = 64/N images per rank, CUDA-graph path),
+`roofline`, `cpu_baseline` (the unmodified reference on one host core), `parity` (fused path vs the reference's rows).
 """
 import argparse
 import json
 import os
 import statistics
+import subprocess
 import sys
 import threading
 import time
@@ -24,9 +30,15 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "post-proc images/s (YOLOv5s 640^2, conf=0.001)"
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
-NCU_TRAFFIC_BYTES = {("yolov5", 640, 64, "dense"): 525095552 + 8164096}  # mean of the two captured launches
 UNIT = "images/s"
+
+CONFIGS = {
+    # BASELINE.json configs[1..4]; batch = images per GPU per step
+    "c2": dict(family="yolov5", img=640, batch=64, what="configs[1]: YOLOv5s decode+NMS, 64 images/GPU at 640^2"),
+    "c3": dict(family="yolox", img=640, batch=256, what="configs[2]: YOLOX-s anchor-free decode (8 400 points), batch 256"),
+    "c4": dict(family="retinanet", img=640, batch=64, what="configs[3]: RetinaNet 640^2 (76 725 anchors/image), batch 64"),
+    "c5": dict(family="yolov5", img=1280, batch=16, what="configs[4]: YOLOv5x 1280^2 (100 800 candidates/image)"),
+}
 
 
 def parse():
@@ -35,28 +47,36 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="images per rank per step")
-    ap.add_argument("--family", default="yolov5")
-    ap.add_argument("--img", type=int, default=640)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="images per rank per step (default: the config's)")
+    ap.add_argument("--family", default="")
+    ap.add_argument("--img", type=int, default=0)
     ap.add_argument("--dist", default="dense", choices=["dense", "sparse", "crowd"])
-    ap.add_argument("--pipeline", type=int, default=3, help="0: serial; 1: NMS kernel of batch i overlaps the filter kernel of batch i+1 on a side stream; 2: same, side stream at high priority; 3: two independent lanes (step i entirely on stream i %% 2)")
-    ap.add_argument("--lanes", type=int, default=4, help="streams (= batches in flight) of --pipeline 3")
-    ap.add_argument("--graph", type=int, default=0, help="replay one captured CUDA graph (memset + filter + NMS) per step and lane")
+    ap.add_argument("--lanes", type=int, default=4, help="batches in flight per rank (one CUDA stream each)")
+    ap.add_argument("--graph", type=int, default=-1, help="replay captured CUDA graphs (-1: when batch <= 16)")
+    ap.add_argument("--gather", default="auto", choices=["auto", "p2p", "nccl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-images", type=int, default=2, help="images in the bounded CPU-baseline sample")
-    return ap.parse_args()
+    ap.add_argument("--no-extras", action="store_true", help="skip the sparse/crowd/strong-scaling sub-measurements")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    args.family = args.family or cfg["family"]
+    args.img = args.img or cfg["img"]
+    args.batch = args.batch or cfg["batch"]
+    return args
 
 
-def workload_config(args, world):
+def workload_config(args, world, batch=None, dist_name=None):
+    batch = batch or args.batch
     return {
         "workload": f"{args.family} {args.img}x{args.img} decode+filter+top-k+class-aware NMS, "
-                    f"{args.batch} images/GPU/step, 80 classes, conf=cls=0.001, iou=0.65, max_det=300, "
-                    f"postprocess_bbox=true, distribution={args.dist}",
-        "images_per_gpu_per_step": args.batch,
-        "global_batch": args.batch * world,
-        "distribution": args.dist,
-        "parallelism": f"image-sharded x{world}" + (", all-gather of kept detections" if world > 1 else ""),
-        "l2": "inputs per step (548 MB at 64 images) exceed the 126 MB L2; streamed once per step",
+                    f"{batch} images/GPU/step, 80 classes, conf=cls=0.001, iou=0.65, max_det=300, "
+                    f"postprocess_bbox=true, distribution={dist_name or args.dist}",
+        "baseline_config": CONFIGS[args.config]["what"],
+        "images_per_gpu_per_step": batch,
+        "global_batch": batch * world,
+        "distribution": dist_name or args.dist,
+        "parallelism": f"image-sharded x{world}" + (", kept detections all-gathered (rows stored into every peer's slot by the NMS kernel)" if world > 1 else ""),
+        "l2": "inputs per step exceed the 126 MB L2 (548 MB at 64 v5s images) and are streamed once per step",
     }
 
 
@@ -128,22 +148,20 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# CPU legs (oracle = plain C/numpy restatement of the reference's algorithm; the only place bench.py touches it)
+# CPU legs.  The reference itself (baseline/ref_worker.py: /root/reference or the staged copy baseline/_ref) always
+# runs in child processes; the oracle port (oracle/) is the second, labelled figure.
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_heads(n_images, args, seed=4321):
-    from yoloseries_b200 import synth
-    return [h.numpy() for h in synth.make_heads(args.family, n_images, args.img, args.img, 80, args.dist, seed, "cpu")]
-
-
-def cpu_images_per_second(heads_np, threads):
-    """Time the reference's CPU algorithm (decode -> filter -> FULL greedy NMS loop, no early stop -> post-filter)
-    on the given synthetic images of the bench workload using `threads` host threads (one image per task)."""
+def port_images_per_second(args, n_images, threads):
+    """The C/numpy port (oracle/) of the same algorithm, full greedy loop like the reference: labelled 'port'."""
     from concurrent.futures import ThreadPoolExecutor
 
     import oracle
-
+    from yoloseries_b200 import synth
+    if args.family != "yolov5":
+        return None
+    oracle.load_library()
     hyp = bench_hyp()
-    n_images = heads_np[0].shape[0]
+    heads_np = [h.numpy() for h in synth.make_heads("yolov5", n_images, args.img, args.img, 80, args.dist, 4321, "cpu")]
 
     def one(i):
         dec = oracle.decode_yolov5([h[i:i + 1] for h in heads_np])
@@ -157,81 +175,120 @@ def cpu_images_per_second(heads_np, threads):
         with ThreadPoolExecutor(max_workers=threads) as ex:
             list(ex.map(one, range(n_images)))
     dt = time.perf_counter() - t0
-    return n_images / dt, dt
+    return {"value": n_images / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n_images} images, C/numpy port of the reference algorithm (oracle/), full greedy NMS loop, {dt:.1f} s"}
 
 
-def parity_counters(args, pp, heads, slot, hyp, n_check=2):
-    """North-star parity report on the first images of the bench batch (oracle = checker only, outside the timed
-    region): decoded max relative error vs the numpy restatement, kept rows / candidate indices vs the oracle applied
-    to the GPU-decoded tensor, and how many visited IoUs sit within 1e-6 of the threshold."""
-    import numpy as np
-    import oracle
-    import torch
-
-    sub = [h[:n_check].contiguous() for h in heads]
-    dec_gpu = pp.decode(sub, args.img, args.img).cpu().numpy()
-    dec_ref = oracle.decode_yolov5([h.cpu().numpy() for h in sub])
-    rel = np.abs(dec_gpu - dec_ref) / np.maximum(np.abs(dec_ref), 1.0)
-    want = oracle.evaluator_nms("yolov5", dec_gpu, hyp)
-    torch.cuda.synchronize()
-    rows_ok = idx_ok = True
-    near = 0
-    cnt = slot.cnt[:n_check].cpu().numpy()
-    for i, w in enumerate(want):
-        k = int(cnt[i])
-        got_rows = slot.dets[i, :max(k, 0)].cpu().numpy()
-        got_idx = slot.idx[i, :max(k, 0)].cpu().numpy()
-        if w.rows is None:
-            rows_ok &= k < 0
-            continue
-        rows_ok &= got_rows.shape == w.rows.shape and bool(np.array_equal(got_rows, w.rows))
-        idx_ok &= bool(np.array_equal(got_idx, w.cand_index))
-        order = np.lexsort((np.arange(len(w.nms_scores)), -w.nms_scores.astype(np.float64)))[:4096]
-        iou = oracle.numba_iou(w.nms_boxes[np.asarray(w.keep, dtype=np.int64)], w.nms_boxes[order])
-        near += int(np.sum(np.abs(iou - hyp["iou_threshold"]) < 1e-6))
-    return {"images_checked": n_check, "decoded_max_rel_err": float(rel.max()), "decoded_within_1e-5": bool(rel.max() <= 1e-5),
-            "kept_rows_bit_exact": bool(rows_ok), "kept_indices_bit_exact": bool(idx_ok),
-            "iou_within_1e-6_of_threshold": near}
+def reference_available():
+    from oracle import refharness
+    return os.path.isdir(os.path.join(refharness.REFERENCE_ROOT, "trainer"))
 
 
 def run_reference(args):
+    """The reference arm: the UNMODIFIED reference's XEvaluator.__call__ (do_inference + numba_nms) on the host cores,
+    one single-threaded process per core (the reference is single-threaded), one image per process and step."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    if args.family != "yolov5":
-        print(json.dumps({"impl": "reference", "unavailable": "reference arm implemented for the yolov5 headline config"}))
+    if not reference_available():
+        print(json.dumps({"impl": "reference", "unavailable": "neither /root/reference nor baseline/_ref (staged copy) is present"}))
         return
-    import oracle
-    oracle.load_library()
-    threads = os.cpu_count() or 1
-    budget_s = 240.0
-    warm = min(args.warmup, 1)
-    t_first = None
-    heads_np = cpu_heads(threads, args)  # generated once; every step processes the same `threads` images
-    for _ in range(warm):
-        _, t_first = cpu_images_per_second(heads_np, threads)
-    done, total_t = 0, 0.0
-    for k in range(args.steps):
-        _, dt = cpu_images_per_second(heads_np, threads)
-        done += 1
-        total_t += dt
-        if total_t + (t_first or 0.0) > budget_s:
-            break
-    value = threads * done / total_t
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import ref_worker
+    procs = os.cpu_count() or 1
+    # RetinaNet 640^2 and v5x 1280^2 cost minutes per image on one core: one step is then the whole bounded sample
+    res = ref_worker.throughput(args.family, args.img, args.dist, procs, max(args.steps, 1), min(args.warmup, 1), 150.0)
+    value = res["images_per_s"]
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": done,
-        "steps_requested": args.steps, "warmup": warm, "ms_per_step": 1e3 * total_t / done, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (+f64 IoU)", "data": "synthetic",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": res["steps"],
+        "steps_requested": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * res["seconds"] / res["steps"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (+f64 IoU)", "data": "synthetic",
         "config": workload_config(args, 1),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{threads} images per step, one per host thread, full greedy NMS loop as "
-                                   "utils/nms.py runs it (no early stop); C/numpy port of the reference algorithm "
-                                   "(the reference itself is Python+numba and cannot travel to this box)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "reference",
+                         "sample": f"{procs} images per step (one per single-threaded process, the reference is "
+                                   f"single-threaded), {res['steps']} step(s), {res['seconds']:.1f} s; unmodified "
+                                   "trainer/eval_*.py XEvaluator.__call__ = do_inference + numba_nms (utils/nms.py:10-27, "
+                                   "full greedy loop, truncation to max_det afterwards); numba JIT and imports "
+                                   f"({res['setup_s']:.0f} s) outside the timing",
+                         "s_per_image_1core": res["s_per_image_1core"], "kept_rows": res["kept_rows"][:4]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    try:
+        port = port_images_per_second(args, procs, procs)
+        if port:
+            line["cpu_port"] = port
+    except Exception as e:  # the port is a courtesy figure
+        line["cpu_port"] = {"unavailable": repr(e)}
     print(json.dumps(line))
+
+
+def reference_children(args, seed=4321):
+    """Starts the two 1-image reference runs of the N=1 bench (child processes): mode A (CPU, timed = cpu_baseline) and
+    mode B (hyp['device']='cuda', the parity oracle).  Returns a function that waits and returns their npz paths."""
+    import tempfile
+    tmp = tempfile.mkdtemp(prefix="ysb_bench_ref_")
+    env = dict(os.environ, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    procs = {}
+    for mode, dev in (("A", "cpu"), ("B", "cuda")):
+        out = os.path.join(tmp, f"{mode}.npz")
+        cmd = [sys.executable, os.path.join(ROOT, "baseline", "ref_worker.py"), "case", "--family", args.family,
+               "--img", str(args.img), "--dist", args.dist, "--batch", "1", "--seed", str(seed), "--device", dev,
+               "--out", out]
+        # mode A: no GPU visible to the child (the reference's GPUAnchor picks 'cuda' whenever one is, utils/anchor.py:138)
+        e = dict(env, CUDA_VISIBLE_DEVICES="") if mode == "A" else env
+        procs[mode] = (out, subprocess.Popen(cmd, cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+
+    def wait():
+        res = {}
+        for mode, (out, p) in procs.items():
+            try:
+                so, se = p.communicate(timeout=900)
+            except subprocess.TimeoutExpired:
+                p.kill()
+                res[mode] = {"error": "timeout"}
+                continue
+            if p.returncode != 0:
+                res[mode] = {"error": se[-400:]}
+            else:
+                res[mode] = {"npz": out, "timing": json.loads(so.strip().splitlines()[-1])}
+        return res
+    return wait
+
+
+def parity_vs_reference(args, npz_path, seed=4321):
+    """Fused CUDA path on the same single image the reference child processed; stage-attributed counters."""
+    import ast
+
+    import numpy as np
+    import torch
+
+    from oracle import parity
+    from yoloseries_b200 import synth
+    from yoloseries_b200.engine import PostProcessor
+    g = dict(np.load(npz_path, allow_pickle=False))
+    hyp = bench_hyp(args.family)
+    heads = synth.make_heads(args.family, 1, args.img, args.img, 80, args.dist, seed, "cpu")
+    heads = [h.cuda() for h in heads] if isinstance(heads, list) else tuple(h.cuda() for h in heads)
+    anchors = torch.tensor(synth.V5_ANCHORS_PX) if args.family in ("yolov5", "yolov7") else None
+    pp = PostProcessor(args.family, hyp, anchors=anchors)
+    dec = pp.decode(heads, args.img, args.img).cpu().numpy()
+    rel = np.abs(dec - g["decoded"]) / np.maximum(np.abs(g["decoded"]), 1.0)
+    keys, counts = pp.filter_only(heads, args.img, args.img)
+    rows, idx = pp.to_list(pp.run(heads, args.img, args.img), as_numpy=True, with_index=True)
+    rc = int(g["counts"][0])
+    rep = parity.image_report(args.family, hyp, g["decoded"][0], g["rows"][0, :max(rc, 0)], rc,
+                              keys.cpu().numpy().view(np.uint64)[0], int(counts[0, 0].item()),
+                              rows[0] if rows[0] is not None else np.zeros((0, 6), np.float32),
+                              idx[0] if idx[0] is not None else np.zeros((0,), np.int32),
+                              -1 if rows[0] is None else rows[0].shape[0])
+    out = parity.summarize([rep])
+    out["decoded_max_rel_err"] = float(rel.max())
+    out["decoded_within_1e-5"] = bool(rel.max() <= 1e-5)
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -244,7 +301,8 @@ def run_ours(args):
     import torch.distributed as dist
 
     from yoloseries_b200 import _lib, synth
-    from yoloseries_b200.engine import PostProcessor, flatten_heads
+    from yoloseries_b200.dist import ShardedPostProcessor, bind_to_gpu_numa
+    from yoloseries_b200.engine import flatten_heads
     if not os.path.exists(_lib.LIB_PATH):  # fresh checkout: the built library is git-ignored
         if int(os.environ.get("LOCAL_RANK", "0")) == 0:
             from yoloseries_b200 import build as ysb_build
@@ -260,165 +318,17 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (impl=ours) needs a CUDA device: the engine has no CPU fallback")
+    numa_cores = bind_to_gpu_numa(local)   # before any pinned allocation: staging buffers land on the GPU's NUMA node
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
-
-    hyp = bench_hyp(args.family)
-    heads = synth.make_heads(args.family, args.batch, args.img, args.img, 80, args.dist, 1234 + rank, dev)
-    anchors = torch.tensor(synth.V5_ANCHORS_PX) if args.family in ("yolov5", "yolov7") else None
-    pp = PostProcessor(args.family, hyp, anchors=anchors)
-    flat = flatten_heads(args.family, heads)
-    ent = pp._prepare(flat, args.batch, args.img, args.img, _lib.INPUT_RAW_HEADS)
     lib = _lib.load()
-    params, N, out = ent["params"], ent["N"], ent["out"]
-    ptrs = _lib.head_pointer_array(flat)
-    max_det = params.max_det
-    n_row_f = args.batch * max_det * 6
-
-    class Slot:
-        """Intermediates + outputs of one in-flight batch.  `flat_send` = [rows (b, max_det, 6) f32 | counts (b) i32]:
-        the NMS kernel writes straight into it and, at N > 1, it is the fixed-stride send buffer of the all-gather."""
-
-        def __init__(self, send_row=None):
-            self.keys = torch.empty((args.batch, N), dtype=torch.int64, device=dev)
-            self.counts = torch.zeros((args.batch, 4), dtype=torch.int32, device=dev)
-            self.flat_send = send_row if send_row is not None else torch.zeros(n_row_f + args.batch, dtype=torch.float32, device=dev)
-            self.dets = self.flat_send[:n_row_f].view(args.batch, max_det, 6)
-            self.cnt = self.flat_send[n_row_f:].view(torch.int32)
-            self.idx = torch.empty((args.batch, max_det), dtype=torch.int32, device=dev)
-            self.gathered = torch.empty((world, n_row_f + args.batch), dtype=torch.float32, device=dev) if world > 1 else None
-            self.filtered = torch.cuda.Event()
-            self.done = torch.cuda.Event()
-            self.nms_done = torch.cuda.Event()
-
-    # Two slots + two streams: the select/sort/NMS kernel of batch i (64 CTAs, latency-bound) runs on the side stream
-    # while the HBM-bound filter kernel of batch i+1 streams on the main one.  --pipeline 0 serialises them.
-    n_lanes = max(2, args.lanes) if args.pipeline == 3 else 2
-    # mode 3: slot i % L lives on lane i % L.  At N > 1 the L send buffers are rows of ONE tensor, all-gathered once per
-    # L steps (one NCCL launch per cycle instead of per step: the exchange is latency-bound, 461 kB per rank and step).
-    big_send = torch.zeros((n_lanes, n_row_f + args.batch), dtype=torch.float32, device=dev) if args.pipeline == 3 else None
-    big_recv = torch.empty((world, n_lanes, n_row_f + args.batch), dtype=torch.float32, device=dev) if (world > 1 and args.pipeline == 3) else None
-    slots = ([Slot(big_send[i]) for i in range(n_lanes)] if args.pipeline == 3 else [Slot(), Slot()]) if args.pipeline else [Slot()]
-    comm = torch.cuda.Stream(device=dev) if (world > 1 and args.pipeline == 3) else None
-    gathered_ev = torch.cuda.Event()
-
-    def gather_cycle():
-        """all-gather of the L most recent batches' rows+counts on the comm stream"""
-        for sl_ in slots:
-            comm.wait_event(sl_.nms_done)
-        with torch.cuda.stream(comm):
-            dist.all_gather_into_tensor(big_recv.view(-1), big_send.view(-1))
-        gathered_ev.record(comm)
-
     stream = torch.cuda.current_stream()
-    side = torch.cuda.Stream(device=dev, priority=-1 if args.pipeline == 2 else 0) if args.pipeline else stream
-
-    def launch_filter(head_ptrs, sl, st):
-        _lib.check(lib.ysb_filter_candidates(ctypes.byref(params), head_ptrs, len(flat), sl.keys.data_ptr(), N,
-                                             sl.counts.data_ptr(), ctypes.c_void_p(st.cuda_stream)),
-                   "ysb_filter_candidates")
-
-    def launch_nms(head_ptrs, sl, st):
-        _lib.check(lib.ysb_select_nms(ctypes.byref(params), head_ptrs, len(flat), sl.keys.data_ptr(), N,
-                                      sl.counts.data_ptr(), sl.dets.data_ptr(), sl.idx.data_ptr(),
-                                      sl.cnt.data_ptr(), ctypes.c_void_p(st.cuda_stream)), "ysb_select_nms")
-
-    step_no = [0]
-    lanes = [torch.cuda.Stream(device=dev) for _ in range(n_lanes)] if args.pipeline == 3 else None
-    graphs = None
-    if args.graph and args.pipeline == 3:
-        # one graph per lane: {zero the counters, filter kernel, NMS kernel} with that lane's buffers baked in
-        launch_filter(ptrs, slots[0], stream)
-        launch_nms(ptrs, slots[0], stream)   # first launches outside capture (function attributes, lazy module load)
-        torch.cuda.synchronize()
-        graphs = []
-        for i in range(n_lanes):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=lanes[i], capture_error_mode="thread_local"):
-                launch_filter(ptrs, slots[i], lanes[i])
-                launch_nms(ptrs, slots[i], lanes[i])
-            graphs.append(g)
-
-    def step(ev=None, head_ptrs=None):
-        head_ptrs = head_ptrs or ptrs
-        sl = slots[step_no[0] % len(slots)]
-        if args.pipeline == 3:
-            # two independent lanes: step i runs filter -> NMS (-> all-gather) in order on stream i % 2, so the NMS
-            # kernel of one step overlaps the filter kernel of the next without any cross-stream event
-            st = lanes[step_no[0] % n_lanes]
-            if graphs is not None and head_ptrs is ptrs and comm is None:
-                gi = step_no[0] % n_lanes
-                step_no[0] += 1
-                with torch.cuda.stream(st):
-                    if ev:
-                        ev[0].record(st)
-                    graphs[gi].replay()
-                    if ev:
-                        for e_ in ev[1:]:
-                            e_.record(st)
-                return sl
-            step_no[0] += 1
-            if ev:
-                ev[0].record(st)
-            launch_filter(head_ptrs, sl, st)
-            if ev:
-                ev[1].record(st)
-                ev[2].record(st)
-            if comm is not None:
-                st.wait_event(gathered_ev)   # the slot's send row may be overwritten only after its cycle was gathered
-            launch_nms(head_ptrs, sl, st)
-            if ev:
-                ev[3].record(st)
-            if comm is not None:
-                sl.nms_done.record(st)
-                if step_no[0] % n_lanes == 0:
-                    gather_cycle()
-            return sl
-        step_no[0] += 1
-        if args.pipeline:
-            stream.wait_event(sl.done)       # the slot's previous batch has left the NMS stage
-        if ev:
-            ev[0].record(stream)
-        launch_filter(head_ptrs, sl, stream)
-        if ev:
-            ev[1].record(stream)
-        if args.pipeline:
-            sl.filtered.record(stream)
-            side.wait_event(sl.filtered)
-        if ev:
-            ev[2].record(side)
-        launch_nms(head_ptrs, sl, side)
-        if ev:
-            ev[3].record(side)
-        if world > 1:
-            with torch.cuda.stream(side):
-                dist.all_gather_into_tensor(sl.gathered.view(-1), sl.flat_send)
-        if args.pipeline:
-            sl.done.record(side)
-        return sl
-
-    def fork():
-        if args.pipeline == 3:  # the lanes start after whatever the main stream has queued (e_beg, H2D copies)
-            for ln in lanes:
-                ln.wait_stream(stream)
-
-    def drain():
-        if args.pipeline == 3:
-            if comm is not None:
-                if step_no[0] % n_lanes != 0:   # a partial last cycle still has to be exchanged
-                    gather_cycle()
-                stream.wait_stream(comm)
-            for ln in lanes:
-                stream.wait_stream(ln)
-        elif args.pipeline:
-            stream.wait_stream(side)
-
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
+    anchors = torch.tensor(synth.V5_ANCHORS_PX) if args.family in ("yolov5", "yolov7") else None
+    hyp = bench_hyp(args.family)
+    graph = None if args.graph < 0 else bool(args.graph)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -426,53 +336,106 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    sync_all()
-    # ---- timed region: exactly K steps, device events, max over ranks -------------------------------------
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
-    e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if sampler:
-        sampler.arm(True)  # sampled through the timed region and the identical-load hold phase that follows it
-    e_beg.record(stream)
-    fork()
-    for k in range(args.steps):
-        step(evs[k])
-    drain()
-    e_end.record(stream)
-    sync_all()
-    total_ms = e_beg.elapsed_time(e_end)
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    # Keep the identical load running ~1.5 s so NVML (10 ms period) sees the clocks this workload runs at.  The number
-    # of extra steps is derived from the (all-reduced) step time, so every rank issues the same collectives.
-    hold_steps = int(min(200000, max(100, 1500.0 / max(total_ms / args.steps, 1e-3))))
-    if sampler:
-        sampler.arm(True)
-    for i in range(hold_steps):
-        step()
-        if i % 64 == 63:
-            drain()
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    class Workload:
+        """Heads of one (batch, distribution) resident in HBM + the package's sharded post-processor for them."""
+
+        def __init__(self, batch, dist_name, seed):
+            self.batch, self.dist_name = batch, dist_name
+            self.heads = synth.make_heads(args.family, batch, args.img, args.img, 80, dist_name, seed, dev)
+            self.flat = flatten_heads(args.family, self.heads)
+            self.spp = ShardedPostProcessor(args.family, hyp, batch, args.img, args.img, anchors=anchors, lanes=args.lanes,
+                                            gather=args.gather, graph=graph)
+
+        def fork(self):
+            for st in self.spp.streams:
+                st.wait_stream(stream)
+
+        def measure(self, steps, warmup, events=False):
+            """Exactly `steps` timed steps bracketed by barrier + synchronize; device time, max over ranks."""
+            spp = self.spp
+            for _ in range(max(warmup, 3)):
+                spp.submit(self.heads, sync_input=False)
+            spp.drain()
+            sync_all()
+            evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)] if events else None
+            e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e_beg.record(stream)
+            self.fork()
+            for k in range(steps):
+                spp.submit(self.heads, events=evs[k] if evs else None, sync_input=False)
+            spp.drain()
+            e_end.record(stream)
+            sync_all()
+            spp.check()
+            total_ms = max_over_ranks(e_beg.elapsed_time(e_end))
+            out = {"total_ms": total_ms, "ms_per_step": total_ms / steps,
+                   "images_per_s": world * self.batch * steps / (total_ms * 1e-3)}
+            if evs:
+                out["filter_ms"] = [e[0].elapsed_time(e[1]) for e in evs]
+                out["nms_ms"] = [e[1].elapsed_time(e[2]) for e in evs]
+            return out
+
+        def filter_alone_ms(self, reps=50):
+            """The dominant kernel by itself (no concurrent NMS kernel), CUDA events around each launch."""
+            spp = self.spp
+            sl, params = spp._slots[0], spp._ent["params"]
+            ptrs = _lib.head_pointer_array(self.flat)
+            iso = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(reps)]
+            for a, b_ in iso:
+                a.record(stream)
+                _lib.check(lib.ysb_filter_candidates(ctypes.byref(params), ptrs, len(self.flat), sl["keys"].data_ptr(),
+                                                     spp._key_cap, sl["counts"].data_ptr(),
+                                                     ctypes.c_void_p(stream.cuda_stream)), "ysb_filter_candidates")
+                b_.record(stream)
             torch.cuda.synchronize()
-    drain()
+            return statistics.mean(a.elapsed_time(b_) for a, b_ in iso)
+
+        def survivors(self):
+            return float(self.spp._slots[0]["counts"][:, 0].float().mean().item())
+
+        def kept(self):
+            rows, cnt = self.spp.gathered(0)
+            return float(cnt[self.spp.rank].clamp(min=0).float().mean().item())
+
+        def close(self):
+            self.spp.close()
+            del self.heads, self.flat
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+
+    main = Workload(args.batch, args.dist, 1234 + rank)
+    main.measure(3, max(args.warmup, 3))   # untimed shake-out: lazy module load, graph capture, peer mappings
+    if sampler:
+        sampler.arm(True)   # sampled through the timed region and the identical-load hold phase that follows it
+    graphed = main.spp.graph
+    timed = main.measure(args.steps, args.warmup, events=not graphed)
+    total_ms = timed["total_ms"]
+    # Keep the identical load running ~1.5 s so NVML (10 ms period) sees the clocks this workload runs at; the step count
+    # is derived from the all-reduced step time, so every rank issues the same sequence.
+    hold_steps = int(min(200000, max(100, 1500.0 / max(total_ms / args.steps, 1e-3))))
+    hold_steps -= hold_steps % 64
+    for i in range(hold_steps):
+        main.spp.submit(main.heads, sync_input=False)
+        if i % 64 == 63:
+            main.spp.drain()
+            torch.cuda.synchronize()
+    main.spp.drain()
     torch.cuda.synchronize()
     if sampler:
         sampler.arm(False)
     sync_all()
-    filt_ms = [e[0].elapsed_time(e[1]) for e in evs]
-    nms_ms = [e[2].elapsed_time(e[3]) for e in evs]
-    # the dominant kernel alone (no concurrent NMS kernel), same inputs, same stream, CUDA events around each launch
-    iso = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(50)]
-    for a, b_ in iso:
-        a.record(stream)
-        launch_filter(ptrs, slots[0], stream)
-        b_.record(stream)
-    torch.cuda.synchronize()
-    iso_ms = statistics.mean(a.elapsed_time(b_) for a, b_ in iso)
-    m_mean = float(slots[0].counts[:, 0].float().mean().item())
-    # every rank's own speed on the HBM-bound kernel: the collectives make all ranks run at the slowest one's pace
+    main.spp.check()
+    iso_ms = main.filter_alone_ms()
+    m_mean = main.survivors()
+    kept_mean = main.kept()
     iso_per_rank = [iso_ms]
     if world > 1:
         tt = torch.tensor([iso_ms], dtype=torch.float64, device=dev)
@@ -480,99 +443,181 @@ def run_ours(args):
         dist.all_gather_into_tensor(allv, tt)
         iso_per_rank = [float(x) for x in allv.tolist()]
 
-    # ---- end-to-end: host (pinned) heads -> H2D -> kernels -> D2H of rows + counts, per step -------------------
-    host_heads = [torch.empty(t_.shape, dtype=t_.dtype, pin_memory=True).copy_(t_) for t_ in flat]
-    dev_heads = [torch.empty_like(t_) for t_ in flat]
-    host_dets = torch.empty((args.batch, max_det, 6), dtype=torch.float32, pin_memory=True)
-    host_cnt = torch.empty((args.batch,), dtype=torch.int32, pin_memory=True)
-    ptrs2 = _lib.head_pointer_array(dev_heads)
+    # ---- end to end through the public API: pinned host heads -> H2D -> kernels (-> peers) -> D2H of rows + counts ----
+    spp = main.spp
+    n_buf = min(2, spp.lanes)
+    host_heads = [torch.empty(t_.shape, dtype=t_.dtype, pin_memory=True).copy_(t_) for t_ in main.flat]
+    dev_bufs = [[torch.empty_like(t_) for t_ in main.flat] for _ in range(n_buf)]
+    b_loc, max_det = args.batch, spp.max_det
+    host_rows = [torch.empty((b_loc, max_det, 6), dtype=torch.float32, pin_memory=True) for _ in range(n_buf)]
+    host_cnt = [torch.empty((b_loc,), dtype=torch.int32, pin_memory=True) for _ in range(n_buf)]
+    copy_streams = [torch.cuda.Stream(device=dev) for _ in range(n_buf)]
+    read_done = [torch.cuda.Event() for _ in range(n_buf)]
 
-    def e2e_step():
-        for d, h in zip(dev_heads, host_heads):
-            d.copy_(h, non_blocking=True)
-        fork()
-        sl = step(None, ptrs2)
-        drain()
-        host_dets.copy_(sl.dets, non_blocking=True)
-        host_cnt.copy_(sl.cnt, non_blocking=True)
-        stream.synchronize()  # the caller reads the rows on the host after every call
+    def rebuild(bufs):
+        """the family's head container around flat device tensors"""
+        if args.family in ("retinanet", "retinanet_exp"):
+            return (bufs[0], bufs[1])
+        if args.family == "fcos":
+            n = len(bufs) // 3
+            return (bufs[:n], bufs[n:2 * n], bufs[2 * n:])
+        return list(bufs)
 
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        e2e_step()
+    def e2e_run(steps):
+        """Step k: H2D of its heads on copy stream k % 2 (overlaps the kernels and the D2H of step k-1), kernels on the
+        package's lane, D2H of this rank's rows + counts; the host waits for step k-1's result while step k is in flight."""
+        pending = None
+        for k in range(steps):
+            j = k % n_buf
+            cs = copy_streams[j]
+            cs.wait_event(read_done[j])            # the kernels that read this staging buffer two steps ago are done
+            with torch.cuda.stream(cs):
+                for d, h in zip(dev_bufs[j], host_heads):
+                    d.copy_(h, non_blocking=True)
+                lane = spp.submit(rebuild(dev_bufs[j]), sync_input=True)
+                rows, cnt = spp.gathered(lane)
+                host_rows[j].copy_(rows[spp.rank], non_blocking=True)
+                host_cnt[j].copy_(cnt[spp.rank], non_blocking=True)
+                read_done[j].record(cs)
+            if pending is not None:
+                read_done[pending].synchronize()   # the caller reads step k-1's rows on the host
+            pending = j
+        read_done[pending].synchronize()
+
+    e2e_steps = max(4, min(args.steps, 12))
+    was_graph = spp.graph
+    spp.graph = False      # the staging buffers alternate: plain launches
+    e2e_run(2)
     sync_all()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
+    e2e_run(e2e_steps)
+    torch.cuda.synchronize()
+    e2e_local_ms = (time.perf_counter() - t0) * 1e3
     sync_all()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
-    h2d = sum(t_.numel() * 4 for t_ in flat)
-    d2h = host_dets.numel() * 4 + host_cnt.numel() * 4
+    e2e_ms = max_over_ranks(e2e_local_ms)
+    spp.graph = was_graph
+    spp.check()
+    h2d = sum(t_.numel() * 4 for t_ in main.flat)
+    d2h = host_rows[0].numel() * 4 + host_cnt[0].numel() * 4
+    del dev_bufs, host_heads
 
     clocks = sampler.stop() if sampler else None
+
+    # ---- the same shape on the other input distributions, and BASELINE's "batch 64 sharded over N GPUs" -----------------
+    extras = {}
+    if not args.no_extras:
+        ex_steps = max(10, min(args.steps, 30))
+        if args.family in ("yolov5", "yolov7") and args.dist == "dense":
+            dists = {}
+            for dname in ("sparse", "crowd"):
+                w = Workload(args.batch, dname, 2234 + rank)
+                r = w.measure(ex_steps, 3)
+                dists[dname] = {"value": r["images_per_s"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "steps": ex_steps,
+                                "survivors_per_image": w.survivors(), "kept_per_image": w.kept(),
+                                "filter_alone_ms": w.filter_alone_ms(20)}
+                w.close()
+            extras["distributions"] = dists
+        if args.config == "c2" and args.batch == 64:
+            per_rank = 64 // world if world > 1 else 8
+            if per_rank >= 1 and (world == 1 or 64 % world == 0):
+                w = Workload(per_rank, args.dist, 3234 + rank)
+                r = w.measure(max(ex_steps, 40), 5)
+                extras["c2_strong"] = {
+                    "what": ("BASELINE configs[1] as written: global batch 64 sharded over %d GPUs = %d images per rank" % (world, per_rank))
+                            if world > 1 else "the 8-images-per-rank shard of configs[1] at 8 GPUs, on one GPU",
+                    "images_per_rank": per_rank, "global_batch": per_rank * world, "value": r["images_per_s"], "unit": UNIT,
+                    "ms_per_step": r["ms_per_step"], "cuda_graph": bool(w.spp.graph), "lanes": w.spp.lanes}
+                w.close()
+
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        C = 80
+        C, N = 80, main.spp._ent["N"]
         # channels the filter kernel must read per candidate: class logits (+ objectness / centerness / conf when the
         # family has one); box channels are not read by it
         n_read_ch = C + (0 if args.family in ("yolov8", "retinanet") else 1)
         algo_bytes = args.batch * (N * n_read_ch * 4 + m_mean * 8)
-        filt_mean_ms = statistics.mean(filt_ms)
-        # With several batches in flight the launches of the dominant kernel overlap each other and the NMS kernels, so
-        # an event-delimited "launch duration" double-counts time.  Its average duration over the timed region is the
-        # region itself divided by the launches it contains: K launches moved K * algo_bytes in total_ms.
-        region_launch_ms = total_ms / args.steps if args.pipeline == 3 else filt_mean_ms
+        # Several batches are in flight, so launches of the dominant kernel overlap each other and the NMS kernels: its
+        # average duration over the timed region is the region divided by the launches it contains.
+        region_launch_ms = total_ms / args.steps
         achieved = algo_bytes / (region_launch_ms * 1e-3) / 1e9
+        kernel = ("k_filter_rows" if args.family in ("yolov7", "retinanet", "retinanet_exp") else
+                  "k_filter_planes_v4" if args.family in ("yolov5", "yolox", "yolov8") else "k_filter_planes")
+        launches_per_step = 4 if spp.mode == "p2p" else 2
         line = {
-            "metric": METRIC, "value": world * args.batch * args.steps / (total_ms * 1e-3), "unit": UNIT,
+            "metric": METRIC, "value": timed["images_per_s"], "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (+f64 IoU test)",
             "data": "synthetic", "config": workload_config(args, world),
             "clocks": clocks,
             "e2e": {"value": world * args.batch * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "api": "host pinned head tensors -> ysb_filter_candidates + ysb_select_nms -> host rows/counts"},
-            "gpu_launches": 2 * args.steps,
+                    "api": "ShardedPostProcessor.submit(heads staged from pinned host memory) -> gathered() -> pinned host rows/counts; "
+                           "H2D of step k+1 overlaps the kernels and D2H of step k (two staging buffers)",
+                    "numa_bound_cores": numa_cores},
+            "gpu_launches": launches_per_step * args.steps,
+            "gather": spp.mode, "lanes": spp.lanes, "cuda_graph": bool(graphed),
             "filter_alone_ms_per_rank": [round(x, 5) for x in iso_per_rank],
-            "roofline": {"kernel": ("k_filter_rows" if args.family in ("yolov7", "retinanet", "retinanet_exp") else "k_filter_planes_v4<9,128,6>" if args.family in ("yolov5", "yolox", "yolov8") else "k_filter_planes<4>")
-                                   + " (decode-sigmoid + filter + class pick + compaction)",
+            "roofline": {"kernel": kernel + " (decode-sigmoid + filter + class pick + compaction)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src,
-                         "traffic": NCU_TRAFFIC_BYTES.get((args.family, args.img, args.batch, args.dist)),
-                         "traffic_source": "profiles/r1_filter_ncu_raw.txt (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture)",
+                         "peak_source": peak_src, "traffic": None,
+                         "traffic_note": "not measurable inside the run; the ncu --set full capture of this kernel is "
+                                         "profiles/r2_filter_ncu_raw.txt (dram__bytes_read.sum + dram__bytes_write.sum)",
                          "launch_ms_alone": iso_ms, "achieved_alone": algo_bytes / (iso_ms * 1e-3) / 1e9,
                          "frac_alone": algo_bytes / (iso_ms * 1e-3) / 1e9 / peak,
                          "note": "achieved/frac: algorithmic bytes of the K filter launches / duration of the timed region "
-                                 "(launches of consecutive batches overlap each other and the NMS kernels, so this is a "
-                                 "lower bound for the kernel); *_alone: the same kernel timed by itself with CUDA events; "
-                                 "launch_ms_overlapped: event-delimited duration of one launch inside the region",
-                         "launch_ms_overlapped": filt_mean_ms,
+                                 "(launches of consecutive batches overlap each other and the NMS kernels); *_alone: the "
+                                 "same kernel timed by itself with CUDA events",
                          "algorithmic_bytes_per_launch": algo_bytes,
                          "bytes_per_image": f"N*{n_read_ch}*4 read + M*8 written = {N * n_read_ch * 4} + {m_mean * 8:.0f}",
                          "launch_ms": region_launch_ms},
-            "pipeline": bool(args.pipeline), "lanes": n_lanes if args.pipeline == 3 else (2 if args.pipeline else 1),
-            "cuda_graph": bool(graphs),
-            "stages_ms": {"filter_compact": filt_mean_ms, "select_sort_nms": statistics.mean(nms_ms),
-                          "filter_p50": statistics.median(filt_ms), "nms_p50": statistics.median(nms_ms)},
-            "survivors_per_image": m_mean,
+            "survivors_per_image": m_mean, "kept_per_image": kept_mean,
         }
-        if not args.no_cpu_baseline and world == 1 and args.family == "yolov5":
-            v, dt = cpu_images_per_second(cpu_heads(args.cpu_images, args), 1)
-            line["cpu_baseline"] = {
-                "value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                "sample": f"{args.cpu_images} images of the same workload on 1 host thread ({dt:.1f} s): C/numpy port "
-                          "of the reference algorithm incl. the full greedy NMS loop (no early stop)"}
-            line["parity"] = parity_counters(args, pp, heads, slots[0], hyp)
+        if "filter_ms" in timed:
+            line["stages_ms"] = {"filter_compact": statistics.mean(timed["filter_ms"]),
+                                 "select_sort_nms": statistics.mean(timed["nms_ms"]),
+                                 "filter_p50": statistics.median(timed["filter_ms"]),
+                                 "nms_p50": statistics.median(timed["nms_ms"])}
+        line.update(extras)
+        if not args.no_cpu_baseline and world == 1:
+            slow = (args.family, args.img) in (("retinanet", 640), ("retinanet_exp", 640)) or args.img > 640
+            if reference_available() and not slow:
+                res = reference_children(args)()
+                a, b_ = res.get("A", {}), res.get("B", {})
+                if "timing" in a:
+                    s_img = a["timing"]["decode_s"] + a["timing"]["nms_s"]
+                    line["cpu_baseline"] = {
+                        "value": 1.0 / s_img, "unit": UNIT, "cores": 1, "kind": "reference",
+                        "sample": f"1 image of the same workload, unmodified reference (do_inference {a['timing']['decode_s']:.3f} s + "
+                                  f"numba_nms {a['timing']['nms_s']:.1f} s) in a single-threaded child process, numba JIT excluded"}
+                else:
+                    line["cpu_baseline"] = {"unavailable": a.get("error", "?")}
+                par = {}
+                for mode, r_ in (("vs_reference_cuda_decode", b_), ("vs_reference_cpu_decode", a)):
+                    if "npz" in r_:
+                        try:
+                            par[mode] = parity_vs_reference(args, r_["npz"])
+                        except Exception as e:
+                            par[mode] = {"error": repr(e)}
+                    else:
+                        par[mode] = {"unavailable": r_.get("error", "?")}
+                line["parity"] = par
+            port = None
+            try:
+                port = port_images_per_second(args, 2, 1)
+            except Exception as e:
+                port = {"unavailable": repr(e)}
+            if port:
+                line["cpu_port"] = port
+                if "cpu_baseline" not in line:
+                    line["cpu_baseline"] = port
         print(json.dumps(line))
+    main.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -40,13 +40,15 @@
 extern "C" {
 #endif
 
-#define YSB_ABI_VERSION 2
+#define YSB_ABI_VERSION 3
 #define YSB_MAX_LEVELS 8
 #define YSB_MAX_ANCHORS 9
 #define YSB_MAX_PASSES 4             /* test-time-augmentation passes merged by ysb_postprocess_tta */
 #define YSB_MAX_DET_LIMIT 1024      /* max_det upper bound (kept list lives in shared memory) */
 #define YSB_MAX_CANDIDATES 4194303  /* candidate index must fit 22 bits of the sort key */
 #define YSB_MAX_CLASSES 1024        /* class id must fit 10 bits of the sort key */
+#define YSB_MAX_PEERS 16            /* ranks (GPUs of one NVLink domain) in a detection gather */
+#define YSB_IPC_HANDLE_BYTES 64     /* sizeof(cudaIpcMemHandle_t) */
 
 typedef enum ysb_status {
     YSB_OK = 0,
@@ -208,6 +210,49 @@ int ysb_soft_nms(const float *d_boxes, const float *d_scores, int64_t m, float i
  * d_info (batch, 5) float32 = {scale, pad_top, pad_left, org_h, org_w}:  x = clamp((x - pad_left) / scale, 1, org_w - 1),
  * y = clamp((y - pad_top) / scale, 1, org_h - 1), float32, one rounding per operation. */
 int ysb_undo_letterbox(float *d_dets, const int32_t *d_det_cnt, int batch, int max_det, const float *d_info, void *stream);
+
+/* ---- multi-GPU: all-gather of the kept detections fused into the NMS kernel ----------------
+ * Images shard over the ranks (one process per GPU); the only exchange on the path is the final all-gather of every
+ * rank's fixed-stride rows (batch, max_det, 6) + counts (batch) for mAP evaluation.  The reference has no such step (its
+ * val sampler is not rank-sliced, dataset/data_sampler.py:185-192; the closest is the unused pickle-over-gloo all_gather
+ * of utils/dist.py:176-211).  Here there is NO collective launch: every rank owns one symmetric receive buffer that its
+ * peers map over NVLink (CUDA IPC), and the NMS kernel's ordered row write stores each row straight into every peer's
+ * slot, followed by one system-scope arrival count per image.  Slots = batches in flight per rank.
+ *
+ *   buffer layout (identical on every rank, zero-initialised):
+ *     rows    [slots][world][batch][max_det][6] f32     cnt  [slots][world][batch] i32
+ *     arrived [slots][world] u32  (images of peer r that have landed in this slot, cumulative)
+ *     ack     [slots][world] u32  (peer r has finished reading use u of MY slot region: I may overwrite it)
+ *     use     [slots] u32 (completed uses of the slot, local)      err [1] u32 (a spin timed out, local)
+ *   per step and slot, all on the caller's stream:
+ *     ysb_gather_begin       zero the filter counters, tell every peer "I have consumed the previous use of this slot"
+ *                            and wait until every peer has said the same (the slot may be overwritten)
+ *     ysb_filter_candidates, ysb_select_nms_gather  (rows + counts -> every peer's slot, then arrival counts)
+ *     ysb_gather_wait        wait until the rows of every rank have landed in MY slot
+ *   Every rank must run the same sequence of (slot) steps.  Spins are bounded (~20 s); a timeout sets `err`, which
+ *   ysb_gather_error reads back (host sync). */
+typedef struct ysb_gather {
+    int32_t world, rank, slots, batch, max_det;
+    void *d_buf[YSB_MAX_PEERS];   /* d_buf[rank] = own buffer (ysb_gather_alloc), the others = ysb_gather_open mappings */
+} ysb_gather;
+
+int ysb_gather_buffer_bytes(int world, int slots, int batch, int max_det, size_t *bytes_out);
+/* cudaMalloc + zero fill on the current device; handle_out (YSB_IPC_HANDLE_BYTES) is what the peers pass to _open. */
+int ysb_gather_alloc(size_t bytes, void **d_buf_out, unsigned char *handle_out);
+int ysb_gather_open(const unsigned char *handle, void **d_peer_buf_out);
+int ysb_gather_close(void *d_peer_buf);
+int ysb_gather_free(void *d_buf);
+/* pointers into the OWN buffer: rows (world, batch, max_det, 6) f32 and counts (world, batch) i32 of one slot */
+int ysb_gather_slot_views(const ysb_gather *g, int slot, float **d_rows_out, int32_t **d_cnt_out);
+/* the per-rank regions inside a slot are padded to 256 bytes: rank r's rows start r * rows_rank_bytes after d_rows_out */
+int ysb_gather_strides(const ysb_gather *g, int64_t *rows_rank_bytes, int64_t *cnt_rank_bytes);
+int ysb_gather_begin(const ysb_gather *g, int slot, int32_t *d_counts, int64_t n_counts, void *stream);
+/* ysb_select_nms whose rows/counts go to every rank's slot (d_det_idx stays local, may be NULL). */
+int ysb_select_nms_gather(const ysb_params *p, const void *const *d_heads, int num_heads, const uint64_t *d_keys,
+                          int64_t key_capacity, const int32_t *d_counts, const ysb_gather *g, int slot,
+                          int32_t *d_det_idx, void *stream);
+int ysb_gather_wait(const ysb_gather *g, int slot, void *stream);
+int ysb_gather_error(const ysb_gather *g, uint32_t *err_out);
 
 /* (n,4) x (m,4) -> (n,m).  kind NUMBA_F64MIX writes float64 (numba_iou), F32 writes float32 (gpu_iou). */
 int ysb_pairwise_iou(const float *d_b1, int64_t n, const float *d_b2, int64_t m, int iou_kind, void *d_out,

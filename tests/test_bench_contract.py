@@ -18,7 +18,8 @@ def _run(*args, env=None, timeout=300):
 
 
 def test_reference_arm_prints_the_contract_line():
-    r = _run("--impl", "reference", "--steps", "1", "--warmup", "0")
+    # a small YOLOX picture keeps the unmodified reference's O(K*M) numba loop at a fraction of a second per image
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--family", "yolox", "--img", "320")
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
@@ -26,7 +27,7 @@ def test_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["unit"] == "images/s" and d["higher_is_better"] is True
     assert d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0 and d["vs_baseline"] is None
     assert d["gpu_launches"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]

@@ -24,8 +24,10 @@ IOU_NUMBA_F64MIX, IOU_F32, GIOU, DIOU, CIOU = range(5)
 IOU_KIND_IDS = {"numba": IOU_NUMBA_F64MIX, "iou": IOU_F32, "giou": GIOU, "diou": DIOU, "ciou": CIOU}
 CMP_GE, CMP_GT = 0, 1
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 YSB_MAX_PASSES = 4
+YSB_MAX_PEERS = 16
+YSB_IPC_HANDLE_BYTES = 64
 YSB_OK, YSB_ERR_BAD_ARG, YSB_ERR_UNSUPPORTED, YSB_ERR_WORKSPACE, YSB_ERR_CUDA, YSB_ERR_LIMIT = 0, -1, -2, -3, -4, -5
 
 
@@ -62,6 +64,18 @@ class YsbParams(ctypes.Structure):
         ("tta_flip", ctypes.c_int32),
         ("tta_img_h", ctypes.c_int32),
         ("tta_img_w", ctypes.c_int32),
+    ]
+
+
+class YsbGather(ctypes.Structure):
+    """Mirror of ``struct ysb_gather``."""
+    _fields_ = [
+        ("world", ctypes.c_int32),
+        ("rank", ctypes.c_int32),
+        ("slots", ctypes.c_int32),
+        ("batch", ctypes.c_int32),
+        ("max_det", ctypes.c_int32),
+        ("d_buf", ctypes.c_void_p * YSB_MAX_PEERS),
     ]
 
 
@@ -112,6 +126,23 @@ _SIGNATURES = {
     "ysb_elementwise_iou_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
                                                     ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                     ctypes.c_void_p]),
+    "ysb_gather_buffer_bytes": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                               ctypes.POINTER(ctypes.c_size_t)]),
+    "ysb_gather_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]),
+    "ysb_gather_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "ysb_gather_close": (ctypes.c_int, [ctypes.c_void_p]),
+    "ysb_gather_free": (ctypes.c_int, [ctypes.c_void_p]),
+    "ysb_gather_slot_views": (ctypes.c_int, [ctypes.POINTER(YsbGather), ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
+                                             ctypes.POINTER(ctypes.c_void_p)]),
+    "ysb_gather_strides": (ctypes.c_int, [ctypes.POINTER(YsbGather), ctypes.POINTER(ctypes.c_int64),
+                                          ctypes.POINTER(ctypes.c_int64)]),
+    "ysb_gather_begin": (ctypes.c_int, [ctypes.POINTER(YsbGather), ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
+                                        ctypes.c_void_p]),
+    "ysb_select_nms_gather": (ctypes.c_int, [ctypes.POINTER(YsbParams), ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
+                                             ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.POINTER(YsbGather),
+                                             ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "ysb_gather_wait": (ctypes.c_int, [ctypes.POINTER(YsbGather), ctypes.c_int, ctypes.c_void_p]),
+    "ysb_gather_error": (ctypes.c_int, [ctypes.POINTER(YsbGather), ctypes.POINTER(ctypes.c_uint32)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

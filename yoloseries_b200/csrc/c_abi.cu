@@ -12,7 +12,12 @@ namespace ysb {
 cudaError_t launch_filter(const Plan &P, int vec, uint64_t *d_keys, int64_t key_cap, int32_t *d_counts, cudaStream_t stream,
                           bool zero_counts);
 cudaError_t launch_select_nms(const Plan &P, const uint64_t *d_keys, int64_t key_cap, const int32_t *d_counts,
-                              float *d_dets, int32_t *d_det_idx, int32_t *d_det_cnt, cudaStream_t stream);
+                              float *d_dets, int32_t *d_det_idx, int32_t *d_det_cnt, cudaStream_t stream,
+                              const GatherSink *sink = nullptr);
+bool make_gather_sink(const ysb_gather *g, int slot, GatherSink *out);
+bool gather_valid(const ysb_gather *g, int slot);
+cudaError_t launch_gather_begin(const ysb_gather *g, int slot, int32_t *d_counts, int64_t n_counts, cudaStream_t stream);
+cudaError_t launch_gather_wait(const ysb_gather *g, int slot, cudaStream_t stream);
 cudaError_t launch_select_nms_tta(const Plan &P, const ExtraPasses &X, const uint64_t *d_keys, int64_t key_cap,
                                   const int32_t *d_counts, float *d_dets, int32_t *d_det_idx, int32_t *d_det_cnt,
                                   cudaStream_t stream);
@@ -321,8 +326,120 @@ int ysb_select_nms(const ysb_params *p, const void *const *d_heads, int num_head
     Built b;
     const int st = build_plan(p, d_heads, num_heads, &b);
     if (st != YSB_OK) return st;
+    if (key_capacity < key_slots(b.plan)) return YSB_ERR_WORKSPACE;
     return cuda_status(launch_select_nms(b.plan, d_keys, key_capacity, d_counts, d_dets, d_det_idx, d_det_cnt,
                                          static_cast<cudaStream_t>(stream)));
+}
+
+// ---- multi-GPU detection gather (gather_kernels.cu) ------------------------------------------------------------------
+int ysb_gather_buffer_bytes(int world, int slots, int batch, int max_det, size_t *bytes_out)
+{
+    if (!bytes_out || world < 1 || world > YSB_MAX_PEERS || slots < 1 || batch < 0 || max_det <= 0) return YSB_ERR_BAD_ARG;
+    if (max_det > YSB_MAX_DET_LIMIT) return YSB_ERR_LIMIT;
+    *bytes_out = gather_layout(world, slots, batch, max_det).total;
+    return YSB_OK;
+}
+
+int ysb_gather_alloc(size_t bytes, void **d_buf_out, unsigned char *handle_out)
+{
+    if (!d_buf_out || bytes == 0) return YSB_ERR_BAD_ARG;
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return cuda_status(e);
+    e = cudaMemset(p, 0, bytes);
+    if (e == cudaSuccess && handle_out) {
+        cudaIpcMemHandle_t h;
+        static_assert(sizeof(h) == YSB_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+        e = cudaIpcGetMemHandle(&h, p);
+        if (e == cudaSuccess) std::memcpy(handle_out, &h, sizeof(h));
+    }
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return cuda_status(e);
+    }
+    *d_buf_out = p;
+    return YSB_OK;
+}
+
+int ysb_gather_open(const unsigned char *handle, void **d_peer_buf_out)
+{
+    if (!handle || !d_peer_buf_out) return YSB_ERR_BAD_ARG;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    void *p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return cuda_status(e);
+    *d_peer_buf_out = p;
+    return YSB_OK;
+}
+
+int ysb_gather_close(void *d_peer_buf)
+{
+    if (!d_peer_buf) return YSB_ERR_BAD_ARG;
+    return cuda_status(cudaIpcCloseMemHandle(d_peer_buf));
+}
+
+int ysb_gather_free(void *d_buf)
+{
+    if (!d_buf) return YSB_ERR_BAD_ARG;
+    return cuda_status(cudaFree(d_buf));
+}
+
+int ysb_gather_slot_views(const ysb_gather *g, int slot, float **d_rows_out, int32_t **d_cnt_out)
+{
+    if (!gather_valid(g, slot)) return YSB_ERR_BAD_ARG;
+    const GatherLayout L = gather_layout(g->world, g->slots, g->batch, g->max_det);
+    unsigned char *mine = static_cast<unsigned char *>(g->d_buf[g->rank]);
+    // the per-rank regions are contiguous only when their padded sizes equal the raw sizes; report the padded strides
+    // through the layout: rows of rank r start at rows_out + r * rows_rank bytes (ysb_gather_buffer_bytes documents it)
+    if (d_rows_out) *d_rows_out = reinterpret_cast<float *>(mine + L.rows + L.rows_slot * slot);
+    if (d_cnt_out) *d_cnt_out = reinterpret_cast<int32_t *>(mine + L.cnt + L.cnt_slot * slot);
+    return YSB_OK;
+}
+
+int ysb_gather_strides(const ysb_gather *g, int64_t *rows_rank_bytes, int64_t *cnt_rank_bytes)
+{
+    if (!gather_valid(g, 0)) return YSB_ERR_BAD_ARG;
+    const GatherLayout L = gather_layout(g->world, g->slots, g->batch, g->max_det);
+    if (rows_rank_bytes) *rows_rank_bytes = static_cast<int64_t>(L.rows_rank);
+    if (cnt_rank_bytes) *cnt_rank_bytes = static_cast<int64_t>(L.cnt_rank);
+    return YSB_OK;
+}
+
+int ysb_gather_begin(const ysb_gather *g, int slot, int32_t *d_counts, int64_t n_counts, void *stream)
+{
+    if (!gather_valid(g, slot) || n_counts < 0) return YSB_ERR_BAD_ARG;
+    return cuda_status(launch_gather_begin(g, slot, d_counts, n_counts, static_cast<cudaStream_t>(stream)));
+}
+
+int ysb_select_nms_gather(const ysb_params *p, const void *const *d_heads, int num_heads, const uint64_t *d_keys,
+                          int64_t key_capacity, const int32_t *d_counts, const ysb_gather *g, int slot,
+                          int32_t *d_det_idx, void *stream)
+{
+    if (!d_heads || !d_keys || !d_counts) return YSB_ERR_BAD_ARG;
+    Built b;
+    const int st = build_plan(p, d_heads, num_heads, &b);
+    if (st != YSB_OK) return st;
+    if (key_capacity < key_slots(b.plan)) return YSB_ERR_WORKSPACE;
+    GatherSink sink;
+    if (!make_gather_sink(g, slot, &sink)) return YSB_ERR_BAD_ARG;
+    if (g->batch != b.plan.batch || g->max_det != b.plan.max_det) return YSB_ERR_BAD_ARG;
+    return cuda_status(launch_select_nms(b.plan, d_keys, key_capacity, d_counts, nullptr, d_det_idx, nullptr,
+                                         static_cast<cudaStream_t>(stream), &sink));
+}
+
+int ysb_gather_wait(const ysb_gather *g, int slot, void *stream)
+{
+    if (!gather_valid(g, slot)) return YSB_ERR_BAD_ARG;
+    return cuda_status(launch_gather_wait(g, slot, static_cast<cudaStream_t>(stream)));
+}
+
+int ysb_gather_error(const ysb_gather *g, uint32_t *err_out)
+{
+    if (!gather_valid(g, 0) || !err_out) return YSB_ERR_BAD_ARG;
+    const GatherLayout L = gather_layout(g->world, g->slots, g->batch, g->max_det);
+    return cuda_status(cudaMemcpy(err_out, static_cast<unsigned char *>(g->d_buf[g->rank]) + L.err, sizeof(uint32_t),
+                                  cudaMemcpyDeviceToHost));
 }
 
 static size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }

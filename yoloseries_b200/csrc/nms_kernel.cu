@@ -253,7 +253,8 @@ template <bool ARRAY, typename EXTRA>
 __global__ void __launch_bounds__(kThreads, 1)
 k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, const uint64_t *__restrict__ keys_all,
              int64_t key_cap, const int32_t *__restrict__ counts, float *__restrict__ dets,
-             int32_t *__restrict__ det_idx, int32_t *__restrict__ det_cnt, const ArrayArgs aa)
+             int32_t *__restrict__ det_idx, int32_t *__restrict__ det_cnt, const ArrayArgs aa,
+             const __grid_constant__ GatherSink G)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmsSmem &S = *reinterpret_cast<NmsSmem *>(smem_raw);
@@ -265,7 +266,12 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
     if (M <= 0) {
         if (tid == 0) {
             if (ARRAY) *aa.keep_cnt = 0;
-            else det_cnt[img] = -1;  // no survivor: the reference appends None
+            else if (G.world == 0) det_cnt[img] = -1;  // no survivor: the reference appends None
+        }
+        if (!ARRAY && G.world > 0 && tid < G.world) {   // detection gather: the count goes to every rank's slot
+            G.cnt[tid][img] = -1;
+            __threadfence_system();
+            atomicAdd_system(G.arrived[tid], 1u);
         }
         return;
     }
@@ -674,23 +680,43 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
         for (int w = 0; w < (tid >> 5); ++w) before += S.warp_tmp[w];
         if (pass) {
             const int at = before + __popc(bal & ((1u << (tid & 31)) - 1u));
-            float *row = dets + (static_cast<size_t>(img) * max_det + at) * 6;
             const float sc = key_score(key);
-            row[0] = box.x; row[1] = box.y; row[2] = box.z; row[3] = box.w;
-            row[4] = P.topk_sqrt ? sqrtf(sc) : sc;  // FCOS: x[:, 4] = sqrt(x[:, 4]) (trainer/eval_fcos.py:281)
-            row[5] = static_cast<float>(key_cls(key));
+            const float s_out = P.topk_sqrt ? sqrtf(sc) : sc;  // FCOS: x[:, 4] = sqrt(x[:, 4]) (trainer/eval_fcos.py:281)
+            const float c_out = static_cast<float>(key_cls(key));
+            const size_t off = (static_cast<size_t>(img) * max_det + at) * 6;
+            // one destination (the caller's buffer) or, in a detection gather, every rank's receive slot: plain stores,
+            // local or over NVLink; a warp writes 32 consecutive rows = 768 contiguous bytes
+            const int ndst = G.world > 0 ? G.world : 1;
+            for (int d = 0; d < ndst; ++d) {
+                float *row = (G.world > 0 ? G.rows[d] : dets) + off;
+                row[0] = box.x; row[1] = box.y; row[2] = box.z; row[3] = box.w;
+                row[4] = s_out;
+                row[5] = c_out;
+            }
             if (det_idx) det_idx[static_cast<size_t>(img) * max_det + at] = static_cast<int32_t>(key_cand(key));
         }
         K2_STAMP(6);
         if (tid == kThreads - 1) {
             const int total = before + __popc(bal);
-            det_cnt[img] = (total == 0 && P.none_when_empty) ? -1 : total;
+            const int value = (total == 0 && P.none_when_empty) ? -1 : total;
+            if (G.world > 0) {
+                for (int d = 0; d < G.world; ++d) G.cnt[d][img] = value;
+            } else {
+                det_cnt[img] = value;
+            }
+        }
+        if (G.world > 0) {
+            // release: every row / count store of this CTA is ordered before the arrival count each peer will see
+            __threadfence_system();
+            __syncthreads();
+            if (tid < G.world) atomicAdd_system(G.arrived[tid], 1u);
         }
     }
 }
 
 cudaError_t launch_select_nms(const Plan &P, const uint64_t *d_keys, int64_t key_cap, const int32_t *d_counts,
-                              float *d_dets, int32_t *d_det_idx, int32_t *d_det_cnt, cudaStream_t stream)
+                              float *d_dets, int32_t *d_det_idx, int32_t *d_det_cnt, cudaStream_t stream,
+                              const GatherSink *sink)
 {
     if (P.batch == 0) return cudaSuccess;
     // per-device attribute; set on every launch (host-side, sub-microsecond) so that a process driving several
@@ -699,8 +725,11 @@ cudaError_t launch_select_nms(const Plan &P, const uint64_t *d_keys, int64_t key
                                          static_cast<int>(sizeof(NmsSmem)));
     if (e != cudaSuccess) return e;
     ArrayArgs aa{};
+    GatherSink G;
+    if (sink) G = *sink;
+    else memset(&G, 0, sizeof(G));
     k_select_nms<false, NoExtraPasses><<<P.batch, kThreads, sizeof(NmsSmem), stream>>>(
-        P, NoExtraPasses{}, d_keys, key_cap, d_counts, d_dets, d_det_idx, d_det_cnt, aa);
+        P, NoExtraPasses{}, d_keys, key_cap, d_counts, d_dets, d_det_idx, d_det_cnt, aa, G);
     return cudaGetLastError();
 }
 
@@ -714,8 +743,10 @@ cudaError_t launch_select_nms_tta(const Plan &P, const ExtraPasses &X, const uin
                                          static_cast<int>(sizeof(NmsSmem)));
     if (e != cudaSuccess) return e;
     ArrayArgs aa{};
+    GatherSink G;
+    memset(&G, 0, sizeof(G));
     k_select_nms<false, ExtraPasses><<<P.batch, kThreads, sizeof(NmsSmem), stream>>>(P, X, d_keys, key_cap, d_counts, d_dets,
-                                                                                      d_det_idx, d_det_cnt, aa);
+                                                                                      d_det_idx, d_det_cnt, aa, G);
     return cudaGetLastError();
 }
 
@@ -780,8 +811,10 @@ cudaError_t launch_array_nms(const float *d_boxes, const float *d_scores, int64_
     aa.iou_kind = iou_kind;
     aa.cmp = cmp;
     aa.thr32 = static_cast<float>(iou_thr);
+    GatherSink G;
+    memset(&G, 0, sizeof(G));
     k_select_nms<true, NoExtraPasses><<<1, kThreads, sizeof(NmsSmem), stream>>>(P, NoExtraPasses{}, keys, m, counts, nullptr,
-                                                                                 nullptr, nullptr, aa);
+                                                                                 nullptr, nullptr, aa, G);
     return cudaGetLastError();
 }
 
