@@ -115,7 +115,22 @@ def test_argument_validation(lib):
     assert lib.ysb_soft_nms(None, None, 4, 0.3, _lib.GIOU, 0, 0.0, None, 0, None, None) == _lib.YSB_ERR_BAD_ARG
     assert lib.ysb_soft_nms(1, 1, 4, 0.3, _lib.IOU_NUMBA_F64MIX, 0, 0.0, 1, 16, 1, None) == _lib.YSB_ERR_BAD_ARG
     assert lib.ysb_soft_nms(1, 1, 4, 0.3, _lib.DIOU, 1, 0.0, 1, 16, 1, None) == _lib.YSB_ERR_BAD_ARG  # sigma must be > 0
-    assert lib.ysb_soft_nms(1, 1, 4, 0.3, _lib.DIOU, 0, 0.0, 1, 15, 1, None) == _lib.YSB_ERR_WORKSPACE
+    assert lib.ysb_soft_nms(16, 1, 4, 0.3, _lib.DIOU, 0, 0.0, 1, 15, 1, None) == _lib.YSB_ERR_WORKSPACE
+    assert lib.ysb_soft_nms(20, 1, 4, 0.3, _lib.DIOU, 0, 0.0, 1, 16, 1, None) == _lib.YSB_ERR_BAD_ARG  # boxes not 16-byte aligned
+    # detection gather: geometry and struct validation happen before any device call
+    nb = ctypes.c_size_t()
+    assert lib.ysb_gather_buffer_bytes(8, 4, 64, 300, ctypes.byref(nb)) == _lib.YSB_OK
+    assert nb.value >= 4 * 8 * 64 * 300 * 24 + 4 * 8 * 64 * 4
+    assert lib.ysb_gather_buffer_bytes(_lib.YSB_MAX_PEERS + 1, 4, 64, 300, ctypes.byref(nb)) == _lib.YSB_ERR_BAD_ARG
+    assert lib.ysb_gather_buffer_bytes(2, 0, 64, 300, ctypes.byref(nb)) == _lib.YSB_ERR_BAD_ARG
+    assert lib.ysb_gather_buffer_bytes(2, 2, 64, 5000, ctypes.byref(nb)) == _lib.YSB_ERR_LIMIT
+    g = _lib.YsbGather()
+    g.world, g.rank, g.slots, g.batch, g.max_det = 2, 0, 2, 4, 300
+    assert lib.ysb_gather_wait(ctypes.byref(g), 0, None) == _lib.YSB_ERR_BAD_ARG      # peer buffers not mapped
+    assert lib.ysb_gather_begin(ctypes.byref(g), 0, None, 0, None) == _lib.YSB_ERR_BAD_ARG
+    g.d_buf[0], g.d_buf[1] = 256, 512
+    assert lib.ysb_gather_wait(ctypes.byref(g), 2, None) == _lib.YSB_ERR_BAD_ARG      # slot out of range
+    assert lib.ysb_gather_open(None, None) == _lib.YSB_ERR_BAD_ARG
     assert lib.ysb_undo_letterbox(None, None, 0, 300, None, None) == _lib.YSB_OK
     assert lib.ysb_undo_letterbox(None, None, 2, 300, None, None) == _lib.YSB_ERR_BAD_ARG
     assert lib.ysb_undo_letterbox(1, 1, 2, 0, 1, None) == _lib.YSB_ERR_BAD_ARG

@@ -269,12 +269,15 @@ def test_cuda_graph_capture_replays_with_refilled_heads():
 
 
 def test_filter_kernel_variants_emit_the_same_survivors():
-    """The default specialised kernel (every level 128-bit loadable), the generic kernel it replaces there, and the
-    profiling variants (tuning points, cp.async ring, 1-D bulk-copy TMA ring, 2-D tensor-map TMA ring) are selected by
-    environment variables read at library load: run each in a subprocess and compare survivor sets."""
+    """The profiling build (python -m yoloseries_b200.build --variants -> libysb_postproc_variants.so, loaded through
+    YSB_LIBRARY) carries the tuning points of the direct-load kernels, the cp.async ring, the 1-D bulk-copy TMA ring and
+    the 2-D tensor-map TMA ring, selected by environment variables read at library load: every one of them must emit the
+    product kernel's survivor sets.  The product library itself has no such switches (the same variables are ignored)."""
     import os
     import subprocess
     import sys
+    from yoloseries_b200 import build as ysb_build
+    have_variants = os.path.exists(ysb_build.VARIANTS_LIB)
     child = r'''
 import hashlib, sys, torch
 sys.path.insert(0, ".")
@@ -294,8 +297,11 @@ for fam, img in (("yolov5", 320), ("yolox", 256), ("yolov8", 128)):
 '''
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = {}
-    for variant, ppt in (("1", "0"), ("1", "50"), ("1", "37"), ("1", "41"), ("3", "8"), ("3", "43"), ("2", "4"), ("0", "0")):
+    combos = (("1", "0"), ("1", "50"), ("1", "37"), ("1", "41"), ("3", "8"), ("3", "43"), ("2", "4"), ("0", "0"))
+    for variant, ppt in combos if have_variants else (("1", "0"), ("3", "8"), ("0", "0")):
         env = dict(os.environ, YSB_FILTER_VARIANT=variant, YSB_BULK_PPT=ppt)
+        if have_variants and (variant, ppt) != ("1", "0"):
+            env["YSB_LIBRARY"] = ysb_build.VARIANTS_LIB
         r = subprocess.run([sys.executable, "-c", child], cwd=root, env=env, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-1500:]
         outs[(variant, ppt)] = r.stdout.strip().splitlines()[-3:]

@@ -99,3 +99,56 @@ def test_normalise_heads_is_a_no_op_for_reference_outputs_and_fixes_the_rest():
     fcos = ([a], [torch.zeros(2, 4, 8, 8)], [torch.zeros(2, 1, 8, 8).half()])
     f = engine.normalise_heads(fcos)
     assert isinstance(f, tuple) and f[0][0] is a and f[2][0].dtype == torch.float32
+
+
+# ---- full shape validation of the head tensors (the C ABI only sees bare pointers) -----------------------------------
+def _heads(family, b=2, img=64, C=5):
+    return engine.flatten_heads(family, synth.make_heads(family, b, img, img, C, "dense", 3, "cpu"))
+
+
+@pytest.mark.parametrize("family", ["yolov5", "yolov7", "yolox", "yolov8", "retinanet", "retinanet_exp", "fcos"])
+def test_validate_heads_accepts_the_reference_layouts(family):
+    anchors = _anchors() if family in ("yolov5", "yolov7") else None
+    engine.validate_heads(family, _heads(family), 5, anchors, 16)
+
+
+def test_validate_heads_rejects_wrong_geometry():
+    a = _anchors()
+    good = _heads("yolov5")
+    with pytest.raises(ValueError, match="level 0 must be"):     # channel count is not A*(5+C)
+        engine.validate_heads("yolov5", good, 6, a)
+    with pytest.raises(ValueError, match="anchor groups"):       # fewer levels than anchor groups
+        engine.validate_heads("yolov5", good[:2], 5, a)
+    with pytest.raises(ValueError, match="batch"):               # batch differs across levels
+        engine.validate_heads("yolov5", [good[0], good[1][:1], good[2]], 5, a)
+    with pytest.raises(ValueError, match="contiguous float32"):
+        engine.validate_heads("yolov5", [good[0].double(), good[1], good[2]], 5, a)
+    with pytest.raises(ValueError, match="contiguous float32"):
+        engine.validate_heads("yolov5", [good[0].transpose(2, 3), good[1], good[2]], 5, a)
+    reg, cls = _heads("retinanet")
+    with pytest.raises(ValueError, match="expected reg"):        # reg / cls row counts differ
+        engine.validate_heads("retinanet", [reg[:, :-9].contiguous(), cls], 5)
+    with pytest.raises(ValueError, match="expected reg"):        # the 5-column reg tensor belongs to retinanet_exp
+        engine.validate_heads("retinanet_exp", [reg, cls], 5)
+    f = _heads("fcos", img=128)
+    with pytest.raises(ValueError, match="level 1 must be"):
+        bad = list(f)
+        bad[5 + 1] = bad[5 + 1][:, :3].contiguous()
+        engine.validate_heads("fcos", bad, 5)
+    with pytest.raises(ValueError, match=r"\(b, N, 10\)"):
+        engine.validate_heads("yolov5", [torch.zeros(2, 7, 9)], 5, decoded_row_w=10)
+    with pytest.raises(ValueError, match="level 2 must be"):
+        v8 = _heads("yolov8")
+        engine.validate_heads("yolov8", v8[:2] + [v8[2][:, :-1].contiguous()] + v8[3:], 5, None, 16)
+
+
+def test_fcos_stride_follows_hyp_input_size_like_the_reference():
+    """trainer/eval_fcos.py:137 -- level stride = hyp['input_img_size'][0] / fm_h, not actual input height / fm_h."""
+    hyp = oracle.default_hyp(num_class=3)
+    hyp["input_img_size"] = [256, 256]
+    shapes = [(16, 16), (8, 8), (4, 4), (2, 2), (1, 1)]
+    p = engine.make_params("fcos", hyp, 1, 128, 128, shapes)
+    assert [p.level_stride[i] for i in range(5)] == [16.0, 32.0, 64.0, 128.0, 256.0]
+    del hyp["input_img_size"]
+    p = engine.make_params("fcos", hyp, 1, 128, 128, shapes)
+    assert [p.level_stride[i] for i in range(5)] == [8.0, 16.0, 32.0, 64.0, 128.0]

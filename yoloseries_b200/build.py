@@ -29,14 +29,23 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, extra_flags=()):
+VARIANTS_LIB = os.path.join(OUT_DIR, "libysb_postproc_variants.so")
+
+
+def build_variants(verbose=False):
+    """The profiling build: same ABI plus the filter-kernel variants selected by YSB_FILTER_VARIANT / YSB_BULK_PPT
+    (csrc/filter_variants.cuh).  Load it with YSB_LIBRARY=<path>; never the default library."""
+    return build(force=True, verbose=verbose, extra_flags=["-DYSB_PROFILING_VARIANTS"], lib=VARIANTS_LIB, tag=".var")
+
+
+def build(force=False, verbose=False, extra_flags=(), lib=LIB, tag=""):
     if not force and not _stale():
-        return LIB
+        return lib
     os.makedirs(OUT_DIR, exist_ok=True)
     objs = []
 
     def compile_one(src):
-        obj = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
+        obj = os.path.join(OUT_DIR, src.replace(".cu", tag + ".o"))
         cmd = [NVCC, *FLAGS, *extra_flags, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -49,14 +58,17 @@ def build(force=False, verbose=False, extra_flags=()):
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    tmp = LIB + f".tmp{os.getpid()}"   # link next to the target, then rename: other processes never see a partial file
+    tmp = lib + f".tmp{os.getpid()}"   # link next to the target, then rename: other processes never see a partial file
     cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs, "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    os.replace(tmp, LIB)
-    return LIB
+    os.replace(tmp, lib)
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force=True, verbose="-v" in sys.argv, extra_flags=[a for a in sys.argv[1:] if a.startswith("-D")]))
+    if "--variants" in sys.argv:
+        print(build_variants(verbose="-v" in sys.argv))
+    else:
+        print(build(force=True, verbose="-v" in sys.argv, extra_flags=[a for a in sys.argv[1:] if a.startswith("-D")]))

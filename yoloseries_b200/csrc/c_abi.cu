@@ -190,6 +190,10 @@ static int build_plan(const ysb_params *p, const void *const *d_heads, int num_h
         if (p->family == YSB_FCOS) P.obj_src = 0;
     }
 
+    // rows layout: the filter kernel stages a tile of 128 rows in shared memory (filter_kernels.cu, k_filter_rows);
+    // rows wider than ~450 floats would not fit the 227 KB a CTA can opt into
+    if (P.layout == LAYOUT_ROWS && static_cast<size_t>(128) * (P.row_w_in | 1) * sizeof(float) > 227u * 1024u) return YSB_ERR_LIMIT;
+
     out->heads_expected = expected_heads(p);
     out->vec = 1;
     if (P.layout == LAYOUT_PLANES) {
@@ -571,6 +575,7 @@ int ysb_nms(const float *d_boxes, const float *d_scores, int64_t m, double iou_t
             void *stream)
 {
     if (m < 0 || !d_keep_cnt || (m > 0 && (!d_boxes || !d_scores || !d_keep || !d_workspace))) return YSB_ERR_BAD_ARG;
+    if (reinterpret_cast<uintptr_t>(d_boxes) & 15u) return YSB_ERR_BAD_ARG;  // boxes are read as float4
     if (cmp != YSB_CMP_GE && cmp != YSB_CMP_GT) return YSB_ERR_BAD_ARG;
     if (iou_kind < YSB_IOU_NUMBA_F64MIX || iou_kind > YSB_CIOU) return YSB_ERR_BAD_ARG;
     if (m > YSB_MAX_CANDIDATES) return YSB_ERR_LIMIT;
@@ -593,6 +598,7 @@ int ysb_soft_nms(const float *d_boxes, const float *d_scores, int64_t m, float i
                  float sigma, void *d_workspace, size_t workspace_bytes, float *d_processed, void *stream)
 {
     if (m < 0 || (m > 0 && (!d_boxes || !d_scores || !d_workspace || !d_processed))) return YSB_ERR_BAD_ARG;
+    if (reinterpret_cast<uintptr_t>(d_boxes) & 15u) return YSB_ERR_BAD_ARG;  // boxes are read as float4
     if (iou_kind != YSB_GIOU && iou_kind != YSB_DIOU && iou_kind != YSB_CIOU && iou_kind != YSB_IOU_F32) return YSB_ERR_BAD_ARG;
     if (mode != 0 && mode != 1) return YSB_ERR_BAD_ARG;
     if (mode == 1 && !(sigma > 0.0f)) return YSB_ERR_BAD_ARG;
@@ -611,6 +617,7 @@ int ysb_undo_letterbox(float *d_dets, const int32_t *d_det_cnt, int batch, int m
 int ysb_pairwise_iou(const float *d_b1, int64_t n, const float *d_b2, int64_t m, int iou_kind, void *d_out, void *stream)
 {
     if (n < 0 || m < 0 || (n > 0 && m > 0 && (!d_b1 || !d_b2 || !d_out))) return YSB_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_b1) | reinterpret_cast<uintptr_t>(d_b2)) & 15u) return YSB_ERR_BAD_ARG;  // float4 loads
     if (iou_kind != YSB_IOU_NUMBA_F64MIX && iou_kind != YSB_IOU_F32) return YSB_ERR_BAD_ARG;
     return cuda_status(launch_pairwise_iou(d_b1, n, d_b2, m, iou_kind, d_out, static_cast<cudaStream_t>(stream)));
 }

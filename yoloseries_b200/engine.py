@@ -127,8 +127,12 @@ def make_params(family, hyp, batch, img_h, img_w, level_shapes=None, anchors=Non
     p.num_levels = len(level_shapes)
     for i, (h, w) in enumerate(level_shapes):
         p.level_h[i], p.level_w[i] = int(h), int(w)
-        if family in _FIXED_STRIDES:
-            p.level_stride[i] = float(_FIXED_STRIDES[family][i]) if family != "fcos" else float(img_h / h)
+        if family == "fcos":
+            # level_i_stride = self.inp_h / fm_h with inp_h from hyp['input_img_size'], not from the actual input
+            # (trainer/eval_fcos.py:17,137): mirrored, so an input of another size decodes like the reference does
+            p.level_stride[i] = float(int(hyp.get("input_img_size", (img_h, img_w))[0]) / h)
+        elif family in _FIXED_STRIDES:
+            p.level_stride[i] = float(_FIXED_STRIDES[family][i])
         else:
             p.level_stride[i] = float(img_h / h)  # eval_yolox.py:144, eval_yolov8.py:91
     if family in ("yolov5", "yolov7"):
@@ -183,6 +187,71 @@ def preds_postprocess(outputs, info):
     return [None if c < 0 else back[i, :c].copy() for i, c in enumerate(cnt.tolist())]
 
 
+def validate_heads(family, flat, num_class, anchors=None, dfl_bins=16, decoded_row_w=None):
+    """Full shape check of the head tensors against the family's layout (include/ysb_postproc.h, enum ysb_family).  The C
+    ABI receives bare pointers, so this is the only place a wrong channel count / batch / level count can be caught; the
+    reference raises a reshape error in the same situations (e.g. trainer/eval_yolov5.py:194)."""
+    C = int(num_class)
+
+    def bad(msg):
+        raise ValueError(f"{family} heads: {msg}")
+    if not flat:
+        bad("no tensors")
+    b = flat[0].shape[0]
+    for i, t in enumerate(flat):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError("head tensors must be contiguous float32")
+        if t.dim() < 2 or t.shape[0] != b:
+            bad(f"tensor {i} has batch {tuple(t.shape)[:1]}, expected {b}")
+        if t.device != flat[0].device:
+            bad("tensors live on different devices")
+    if decoded_row_w is not None:
+        if len(flat) != 1 or flat[0].dim() != 3 or flat[0].shape[2] != decoded_row_w:
+            raise ValueError(f"decoded tensor must be (b, N, {decoded_row_w}), got {tuple(flat[0].shape)}")
+        return
+    if family in ("yolov5", "yolov7"):
+        if anchors is None:
+            bad("anchors (L, A, 2) are required")
+        L, A = int(anchors.shape[0]), int(anchors.shape[1])
+        if len(flat) != L:
+            bad(f"{len(flat)} levels but {L} anchor groups")
+        for i, t in enumerate(flat):
+            want = (b, A * (5 + C)) if family == "yolov5" else (b, A)
+            if family == "yolov5" and (t.dim() != 4 or tuple(t.shape[:2]) != want):
+                bad(f"level {i} must be (b, {A * (5 + C)}, H, W), got {tuple(t.shape)}")
+            if family == "yolov7" and (t.dim() != 5 or tuple(t.shape[:2]) != want or t.shape[4] != 5 + C):
+                bad(f"level {i} must be (b, {A}, H, W, {5 + C}), got {tuple(t.shape)}")
+    elif family == "yolox":
+        na = flat[0].shape[1] if flat[0].dim() == 5 else -1
+        for i, t in enumerate(flat):
+            if t.dim() != 5 or t.shape[1] != na or t.shape[2] != 5 + C:
+                bad(f"level {i} must be (b, {na}, {5 + C}, H, W), got {tuple(t.shape)}")
+    elif family == "yolov8":
+        for i, t in enumerate(flat):
+            if t.dim() != 4 or t.shape[1] != 4 * int(dfl_bins) + C:
+                bad(f"level {i} must be (b, {4 * int(dfl_bins) + C}, H, W), got {tuple(t.shape)}")
+    elif family in ("retinanet", "retinanet_exp"):
+        w = 5 if family == "retinanet_exp" else 4
+        if len(flat) != 2:
+            bad("expected (reg, cls)")
+        reg, cls = flat
+        if reg.dim() != 3 or reg.shape[2] != w or cls.dim() != 3 or cls.shape[2] != C or reg.shape[1] != cls.shape[1]:
+            bad(f"expected reg (b, N, {w}) and cls (b, N, {C}), got {tuple(reg.shape)} and {tuple(cls.shape)}")
+    elif family == "fcos":
+        if len(flat) % 3:
+            bad("expected three lists (cls, reg, ctr) of equal length")
+        n = len(flat) // 3
+        for i in range(n):
+            c, r, q = flat[i], flat[n + i], flat[2 * n + i]
+            hw = tuple(c.shape[2:])
+            if c.dim() != 4 or c.shape[1] != C or r.dim() != 4 or r.shape[1] != 4 or tuple(r.shape[2:]) != hw or \
+                    q.dim() != 4 or q.shape[1] != 1 or tuple(q.shape[2:]) != hw:
+                bad(f"level {i} must be cls (b, {C}, H, W), reg (b, 4, H, W), ctr (b, 1, H, W), got "
+                    f"{tuple(c.shape)}, {tuple(r.shape)}, {tuple(q.shape)}")
+    else:
+        raise ValueError(f"unknown family {family!r}")
+
+
 class DetectionBuffers:
     """Per-call device outputs: rows (b, max_det, 6), candidate indices (b, max_det), counts (b)."""
 
@@ -211,9 +280,12 @@ class PostProcessor:
         dev = flat[0].device
         if dev.type != "cuda":
             raise RuntimeError("yoloseries_b200 runs on CUDA devices only (no CPU fallback); got " + str(dev))
-        for t in flat:
-            if t.dtype != torch.float32 or not t.is_contiguous():
-                raise ValueError("head tensors must be contiguous float32")
+        if input_kind == _lib.INPUT_RAW_HEADS:
+            validate_heads(self.family, flat, self.hyp["num_class"], self.anchors, self.hyp.get("reg", 16))
+        else:
+            for t in flat:
+                if t.dtype != torch.float32 or not t.is_contiguous():
+                    raise ValueError("head tensors must be contiguous float32")
         shapes = None
         if input_kind == _lib.INPUT_RAW_HEADS and self.family not in ("retinanet", "retinanet_exp"):
             shapes = _level_shapes(self.family, flat, self.hyp["num_class"])
@@ -238,11 +310,16 @@ class PostProcessor:
                        workspace=torch.empty(max(ws.value, 1), dtype=torch.uint8, device=dev),
                        out=DetectionBuffers(batch, params.max_det, dev))
             self._cache[key] = ent
+        if input_kind == _lib.INPUT_RAW_HEADS and self.family in ("retinanet", "retinanet_exp") and flat[0].shape[1] != ent["N"]:
+            raise ValueError(f"{self.family} heads: {flat[0].shape[1]} anchors per image, but a {img_h}x{img_w} input has {ent['N']}")
+        if input_kind == _lib.INPUT_DECODED_ROWS:
+            validate_heads(self.family, flat, self.hyp["num_class"], decoded_row_w=ent["row_w"])
         return ent
 
     @staticmethod
-    def _stream():
-        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    def _stream(dev=None):
+        """torch's current stream ON THE HEADS' DEVICE (not on whatever device happens to be current)."""
+        return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
     # ---- public ops ----------------------------------------------------------------------------------------
     def decode(self, heads, img_h, img_w):
@@ -252,8 +329,10 @@ class PostProcessor:
         ent = self._prepare(flat, batch, img_h, img_w, _lib.INPUT_RAW_HEADS)
         out = torch.empty((batch, ent["N"], ent["row_w"]), dtype=torch.float32, device=flat[0].device)
         ptrs = _lib.head_pointer_array(flat)
-        _lib.check(self._lib.ysb_decode(ctypes.byref(ent["params"]), ptrs, len(flat), out.data_ptr(), self._stream()),
-                   "ysb_decode")
+        dev = flat[0].device
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.ysb_decode(ctypes.byref(ent["params"]), ptrs, len(flat), out.data_ptr(),
+                                            self._stream(dev)), "ysb_decode")
         return out
 
     def run(self, heads, img_h, img_w, decoded=False):
@@ -264,14 +343,14 @@ class PostProcessor:
             return DetectionBuffers(0, int(self.hyp["max_predictions_per_img"]), flat[0].device)
         kind = _lib.INPUT_DECODED_ROWS if decoded else _lib.INPUT_RAW_HEADS
         ent = self._prepare(flat, batch, img_h, img_w, kind)
-        if decoded and (flat[0].dim() != 3 or flat[0].shape[2] != ent["row_w"]):
-            raise ValueError(f"decoded tensor must be (b, N, {ent['row_w']}), got {tuple(flat[0].shape)}")
         out = ent["out"]
         ptrs = _lib.head_pointer_array(flat)
         ws = ent["workspace"]
-        _lib.check(self._lib.ysb_postprocess(ctypes.byref(ent["params"]), ptrs, len(flat), ws.data_ptr(), ws.numel(),
-                                             out.dets.data_ptr(), out.det_idx.data_ptr(), out.det_cnt.data_ptr(),
-                                             self._stream()), "ysb_postprocess")
+        dev = flat[0].device
+        with torch.cuda.device(dev):   # kernels, function attributes and the stream all belong to the heads' device
+            _lib.check(self._lib.ysb_postprocess(ctypes.byref(ent["params"]), ptrs, len(flat), ws.data_ptr(), ws.numel(),
+                                                 out.dets.data_ptr(), out.det_idx.data_ptr(), out.det_cnt.data_ptr(),
+                                                 self._stream(dev)), "ysb_postprocess")
         return out
 
     # ---- test-time augmentation (trainer/eval_yolov5.py:152-179 and the same method of every evaluator) ------------
@@ -295,9 +374,11 @@ class PostProcessor:
         batch, total = ents[0][1]["params"].batch, sum(e["N"] for _, e in ents)
         out = torch.empty((batch, total, ents[0][1]["row_w"]), dtype=torch.float32, device=ents[0][0][0].device)
         off, views = 0, []
+        dev = out.device
         for flat, ent in ents:
-            _lib.check(self._lib.ysb_decode_into(ctypes.byref(ent["params"]), _lib.head_pointer_array(flat), len(flat),
-                                                 out.data_ptr(), total, off, self._stream()), "ysb_decode_into")
+            with torch.cuda.device(dev):
+                _lib.check(self._lib.ysb_decode_into(ctypes.byref(ent["params"]), _lib.head_pointer_array(flat), len(flat),
+                                                     out.data_ptr(), total, off, self._stream(dev)), "ysb_decode_into")
             views.append(out[:, off:off + ent["N"]])
             off += ent["N"]
         return out, views
@@ -324,9 +405,10 @@ class PostProcessor:
         flat_all = [t for flat, _ in ents for t in flat]
         per_pass = (ctypes.c_int32 * n)(*[len(flat) for flat, _ in ents])
         out, ws = bundle["out"], bundle["workspace"]
-        _lib.check(self._lib.ysb_postprocess_tta(bundle["params"], n, _lib.head_pointer_array(flat_all), per_pass,
-                                                 ws.data_ptr(), ws.numel(), out.dets.data_ptr(), out.det_idx.data_ptr(),
-                                                 out.det_cnt.data_ptr(), self._stream()), "ysb_postprocess_tta")
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.ysb_postprocess_tta(bundle["params"], n, _lib.head_pointer_array(flat_all), per_pass,
+                                                     ws.data_ptr(), ws.numel(), out.dets.data_ptr(), out.det_idx.data_ptr(),
+                                                     out.det_cnt.data_ptr(), self._stream(dev)), "ysb_postprocess_tta")
         return out
 
     def capture(self, heads, img_h, img_w, decoded=False):
@@ -363,9 +445,10 @@ class PostProcessor:
         keys = torch.empty((batch, slots), dtype=torch.int64, device=dev)
         counts = torch.empty((batch, 4), dtype=torch.int32, device=dev)
         ptrs = _lib.head_pointer_array(flat)
-        _lib.check(self._lib.ysb_filter_candidates(ctypes.byref(ent["params"]), ptrs, len(flat), keys.data_ptr(),
-                                                   slots, counts.data_ptr(), self._stream()),
-                   "ysb_filter_candidates")
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.ysb_filter_candidates(ctypes.byref(ent["params"]), ptrs, len(flat), keys.data_ptr(),
+                                                       slots, counts.data_ptr(), self._stream(dev)),
+                       "ysb_filter_candidates")
         return keys, counts
 
     def undo_letterbox(self, out, info):
@@ -378,10 +461,12 @@ class PostProcessor:
             return out
         if len(info) != out.det_cnt.numel():
             raise ValueError(f"need one info dict per image: {len(info)} != {out.det_cnt.numel()}")
-        table = torch.tensor(letterbox_table(info), dtype=torch.float32).to(out.dets.device, non_blocking=True)
-        _lib.check(self._lib.ysb_undo_letterbox(out.dets.data_ptr(), out.det_cnt.data_ptr(), out.dets.shape[0],
-                                                out.dets.shape[1], table.data_ptr(), self._stream()),
-                   "ysb_undo_letterbox")
+        dev = out.dets.device
+        table = torch.tensor(letterbox_table(info), dtype=torch.float32).to(dev, non_blocking=True)
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.ysb_undo_letterbox(out.dets.data_ptr(), out.det_cnt.data_ptr(), out.dets.shape[0],
+                                                    out.dets.shape[1], table.data_ptr(), self._stream(dev)),
+                       "ysb_undo_letterbox")
         return out
 
     @staticmethod

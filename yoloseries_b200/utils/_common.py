@@ -24,7 +24,10 @@ def to_cuda_f32(x, device=None):
     t = x.detach()
     if t.device.type != "cuda":
         t = t.to(device or cuda_device())
-    return t.to(torch.float32).contiguous()
+    t = t.to(torch.float32).contiguous()
+    if t.data_ptr() % 16:   # an offset view of a larger buffer: the kernels read boxes as float4
+        t = t.clone()
+    return t
 
 
 def nms_indices(boxes, scores, iou_threshold, iou_kind, cmp, max_keep=0):
