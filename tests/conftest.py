@@ -43,10 +43,30 @@ def pytest_collection_modifyitems(config, items):
 
 def golden_names(prefix=""):
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    # tta_* fixtures hold three head sets and the merged tensor, cpu_* fixtures pin the oracle only (their GPU
-    # parametrisation comes with the next GPU-verified change): both are asked for explicitly, golden_names("tta_")
+    # tta_* fixtures hold three head sets and the merged tensor, c1_* fixtures are seed-only full-size cases (heads are
+    # regenerated, see full_size_golden): both are asked for explicitly, golden_names("tta_") / golden_names("c1_")
     return [n for n in names if n.startswith(prefix) and n != "utils_nms_iou"
-            and (prefix or not n.startswith(("tta_", "cpu_")))]
+            and (prefix or not n.startswith(("tta_", "c1_")))]
+
+
+def full_size_golden(name):
+    """c1_* fixture -> (data, heads regenerated on the CPU generator and checked against the stored checksum, the
+    reference's decoded tensor rebuilt from its stored pre-mask survivors or None)."""
+    import hashlib
+
+    from yoloseries_b200 import synth
+    g = load_golden(name)
+    meta = g["meta"]
+    heads = synth.make_heads(meta["family"], 1, meta["img"], meta["img"], meta["num_class"], meta["dist"], meta["seed"], "cpu")
+    sha = hashlib.sha1()
+    for h in heads:
+        sha.update(np.ascontiguousarray(h.numpy()).tobytes())
+    assert sha.hexdigest() == str(g["heads_sha1"]), "synthetic heads drifted from the ones the fixture was generated with"
+    decoded = None
+    if "decoded_rows" in g:
+        decoded = np.zeros(tuple(int(x) for x in g["decoded_shape"]), dtype=np.float32)
+        decoded[0, g["decoded_index"]] = g["decoded_rows"]
+    return g, heads, decoded
 
 
 def load_golden(name):

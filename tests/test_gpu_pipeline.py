@@ -167,3 +167,27 @@ def test_bench_workload_properties(dist, pp_bbox):
     alone = pp.to_list(PostProcessor("yolov5", hyp, anchors=torch.tensor(synth.V5_ANCHORS_PX)).run(
         [h[5:6].contiguous() for h in heads], 640, 640), as_numpy=True)[0]
     assert (alone is None and rows[5] is None) or np.array_equal(alone, rows[5])
+
+
+@pytest.mark.parametrize("name", golden_names("c1_"))
+def test_full_size_reference_fixture_on_gpu(name):
+    """BASELINE C1 size, pinned to the REFERENCE (not only to the oracle): M > 4 096 survivors means radix selection, and
+    the deep-crowd case walks several selection tranches before the 300th keep.
+    (ii) the reference's decoded tensor through the decoded-rows kernels == the reference's rows, bit-exact;
+    (iv) the regenerated raw heads through the fused kernels keep the same candidates in the same order, row values within
+    1e-5 (the fixture was generated with CPU ATen sigmoid/exp, which differ from CUDA's by an ulp)."""
+    from conftest import full_size_golden
+    g, heads, decoded = full_size_golden(name)
+    meta = g["meta"]
+    pp, hyp = _processor(meta)
+    cnt = int(g["counts"][0])
+    want_rows, want_idx = g["rows"][0, :cnt], g["cand_index"][0]
+    if decoded is not None:
+        rows, idx = pp.to_list(pp.run(_to_dev(decoded), meta["img"], meta["img"], decoded=True), as_numpy=True, with_index=True)
+        np.testing.assert_array_equal(rows[0], want_rows)
+        np.testing.assert_array_equal(idx[0], want_idx)
+    dev_heads = [h.cuda() for h in heads]
+    rows, idx = pp.to_list(pp.run(dev_heads, meta["img"], meta["img"]), as_numpy=True, with_index=True)
+    np.testing.assert_array_equal(idx[0], want_idx)
+    assert close_rel(rows[0], want_rows, 1e-5).all()
+    np.testing.assert_array_equal(rows[0][:, 5], want_rows[:, 5])

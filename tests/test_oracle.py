@@ -206,3 +206,27 @@ def test_iou_backward_matches_reference_autograd():
         d1, d2 = oracle.iou_backward(kind, b1[:1], b2, w)
         assert d1.shape == (1, 4)
         assert np.abs(d1 - g[f"grad_{kind}_row_d1"]).max() <= 2e-7 and np.abs(d2 - g[f"grad_{kind}_row_d2"]).max() <= 2e-7
+
+
+@pytest.mark.parametrize("name", golden_names("c1_"))
+def test_full_size_reference_fixture(name):
+    """BASELINE C1 size (25 200 candidates), generated by the unmodified reference: M > 4 096 survivors, and in the
+    deep-crowd case the 300th keep sits thousands of sorted ranks deep.  The oracle on the reference's decoded tensor
+    reproduces the reference's rows bit for bit; on its own numpy decode of the regenerated heads it keeps the same
+    candidates."""
+    from conftest import full_size_golden
+    g, heads, decoded = full_size_golden(name)
+    meta = g["meta"]
+    hyp = hyp_from_meta(meta)
+    cnt = int(g["counts"][0])
+    assert int(g["survivors"]) > 4096
+    if meta["dist"] == "deepcrowd":
+        assert int(g["deepest_keep_rank"]) > 4096          # beyond one selection tranche of the CUDA kernel
+    if decoded is not None:
+        r = oracle.evaluator_nms(meta["family"], decoded, hyp, full_nms=True)[0]
+        np.testing.assert_array_equal(r.rows, g["rows"][0, :cnt])
+        np.testing.assert_array_equal(r.cand_index, g["cand_index"][0])
+    own = oracle.decode_yolov5([h.numpy() for h in heads], num_class=meta["num_class"])
+    r = oracle.evaluator_nms(meta["family"], own, hyp)[0]
+    np.testing.assert_array_equal(r.cand_index, g["cand_index"][0])
+    assert close_rel(r.rows, g["rows"][0, :cnt], 1e-5).all()

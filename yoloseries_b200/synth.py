@@ -11,6 +11,9 @@ shapes -- SURVEY.md section 8d).  Three value distributions:
   crowd   (anchor-grid families) G objects, each written into up to 36 candidates through
           the inverse decode with small jitter; background objectness -12.  Real
           suppression depth for the NMS stage.
+  deepcrowd  the same with 320 objects of 20-34 px (they fit nearly every anchor, ~30 near-identical
+          duplicates each, jitter 0.4 px, one confidence level per object): M ~ 7 000 and the 300th
+          keep sits thousands of sorted ranks deep -- the NMS walk crosses several selection tranches.
 
 Layouts (C = num_class):
   yolov5  list of (b, 3*(5+C), H, W)            strides 8,16,32   utils/layer_tools.py:454-470
@@ -61,10 +64,14 @@ def make_heads(family, batch, img_h=640, img_w=640, num_class=80, dist="dense", 
     g = _gen(seed, device)
     C = num_class
     shapes = level_shapes(family, img_h, img_w)
-    if dist == "crowd":
+    if dist in ("crowd", "deepcrowd"):
         if family not in ("yolov5", "yolov7"):
-            raise ValueError("crowd distribution is implemented for the anchor-grid families")
-        heads = _crowd_v5(batch, shapes, C, g, device)
+            raise ValueError("crowd distributions are implemented for the anchor-grid families")
+        if dist == "crowd":
+            heads = _crowd_v5(batch, shapes, C, g, device)
+        else:
+            heads = _crowd_v5(batch, shapes, C, g, device, objects_per_image=330, jitter_px=0.4, jitter_log=0.01,
+                              size_lo=20.0, size_span=1.7, per_object_score=True)
         if family == "yolov7":
             heads = [h.view(batch, 3, 5 + C, h.shape[2], h.shape[3]).permute(0, 1, 3, 4, 2).contiguous() for h in heads]
         return heads
@@ -120,7 +127,8 @@ def _logit(p):
     return torch.log(p) - torch.log1p(-p)
 
 
-def _crowd_v5(batch, shapes, C, g, device, objects_per_image=700):
+def _crowd_v5(batch, shapes, C, g, device, objects_per_image=700, jitter_px=3.0, jitter_log=0.08, size_lo=16.0,
+              size_span=12.0, per_object_score=False):
     """Objects written through the inverse of the v5 decode (trainer/eval_yolov5.py:203-205)."""
     strides = FAMILY_STRIDES["yolov5"]
     img_w = shapes[0][1] * strides[0]
@@ -135,9 +143,12 @@ def _crowd_v5(batch, shapes, C, g, device, objects_per_image=700):
         G = objects_per_image
         cx = torch.rand(G, generator=g, device=device) * (img_w - 64) + 32
         cy = torch.rand(G, generator=g, device=device) * (img_h - 64) + 32
-        bw = torch.exp(torch.rand(G, generator=g, device=device) * math.log(12.0)) * 16.0
+        bw = torch.exp(torch.rand(G, generator=g, device=device) * math.log(size_span)) * size_lo
         bh = bw * torch.exp(_randn((G,), g, device, std=0.35))
         cls_id = torch.randint(0, C, (G,), generator=g, device=device)
+        # per_object_score: every object has its own confidence level shared by all its duplicates, so the duplicates of a
+        # confident object precede the first candidate of a less confident one in the NMS visiting order
+        base = (torch.rand(G, generator=g, device=device) * 9.0 - 4.0) if per_object_score else None
         for lvl, ((h, w), s) in enumerate(zip(shapes, strides)):
             for a in range(3):
                 aw, ah = anchors[lvl, a, 0], anchors[lvl, a, 1]
@@ -151,10 +162,10 @@ def _crowd_v5(batch, shapes, C, g, device, objects_per_image=700):
                         if idx.numel() == 0:
                             continue
                         n = idx.numel()
-                        jx = cx[idx] + _randn((n,), g, device, std=3.0)
-                        jy = cy[idx] + _randn((n,), g, device, std=3.0)
-                        jw = bw[idx] * torch.exp(_randn((n,), g, device, std=0.08))
-                        jh = bh[idx] * torch.exp(_randn((n,), g, device, std=0.08))
+                        jx = cx[idx] + _randn((n,), g, device, std=jitter_px)
+                        jy = cy[idx] + _randn((n,), g, device, std=jitter_px)
+                        jw = bw[idx] * torch.exp(_randn((n,), g, device, std=jitter_log))
+                        jh = bh[idx] * torch.exp(_randn((n,), g, device, std=jitter_log))
                         px = ((jx / s - gx[idx].float()) + 0.5) / 2.0
                         py = ((jy / s - gy[idx].float()) + 0.5) / 2.0
                         pw = torch.sqrt(jw / aw) / 2.0
@@ -165,9 +176,12 @@ def _crowd_v5(batch, shapes, C, g, device, objects_per_image=700):
                         tgt[1, yy, xx] = _logit(py)
                         tgt[2, yy, xx] = _logit(pw)
                         tgt[3, yy, xx] = _logit(ph)
-                        tgt[4, yy, xx] = _randn((n,), g, device, mean=2.0, std=1.5)
+                        if per_object_score:
+                            tgt[4, yy, xx] = base[idx] + _randn((n,), g, device, std=0.1)
+                        else:
+                            tgt[4, yy, xx] = _randn((n,), g, device, mean=2.0, std=1.5)
                         tgt[5:, yy, xx] = _randn((C, n), g, device, mean=-4.0, std=1.0)
-                        tgt[5 + cls_id[idx], yy, xx] = _randn((n,), g, device, mean=2.5, std=1.0)
+                        tgt[5 + cls_id[idx], yy, xx] = _randn((n,), g, device, mean=2.5, std=0.05 if per_object_score else 1.0)
     return [t.view(batch, 3 * (5 + C), t.shape[3], t.shape[4]).contiguous() for t in heads]
 
 
