@@ -14,6 +14,6 @@ hyp = synth.map_profile_hyp(num_class=80)
 anchors = torch.tensor(synth.V5_ANCHORS_PX) if fam in ("yolov5", "yolov7") else None
 pp = PostProcessor(fam, hyp, anchors=anchors)
 sets = [synth.make_heads(fam, batch, 640, 640, 80, "dense", seed=40 + k, device="cuda") for k in range(3)]
-for i in range(6):
+for i in range(9):
     pp.filter_only(sets[i % 3], 640, 640)
 torch.cuda.synchronize()

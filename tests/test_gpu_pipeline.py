@@ -186,6 +186,8 @@ def test_full_size_reference_fixture_on_gpu(name):
         rows, idx = pp.to_list(pp.run(_to_dev(decoded), meta["img"], meta["img"], decoded=True), as_numpy=True, with_index=True)
         np.testing.assert_array_equal(rows[0], want_rows)
         np.testing.assert_array_equal(idx[0], want_idx)
+    if heads is None:
+        pytest.skip("the CPU generator of this machine does not reproduce the fixture's heads (checksum mismatch)")
     dev_heads = [h.cuda() for h in heads]
     rows, idx = pp.to_list(pp.run(dev_heads, meta["img"], meta["img"]), as_numpy=True, with_index=True)
     np.testing.assert_array_equal(idx[0], want_idx)

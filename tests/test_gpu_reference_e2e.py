@@ -156,8 +156,11 @@ def test_fused_path_vs_reference_cuda_mode_b(case, reference_runs):
     assert _decode_ok(case["family"], dec, ref_dec, case["img"]), "decoded tensor beyond 1e-5 of the reference's"
     fam = case["family"]
     for r in reps:
-        if fam.startswith("retinanet"):
+        if fam.startswith("retinanet") or fam == "yolov8":
+            # RetinaNet: merged boxes come from an sgemm whose summation order is unspecified; YOLOv8: ATen's CUDA softmax
+            # reduces the 16 DFL bins in another order than the sequential sum of the CPU path this engine mirrors
             assert r.get("kept_indices_equal", r.get("rows_bit_exact")) and r.get("rows_max_rel_err", 0.0) <= 1e-5, (r, summary)
+            assert r.get("score_bits_differ", 0) == 0 and r["stage"] in ("ok", "rows"), (r, summary)
         else:
             assert r["stage"] == "ok" and r["rows_bit_exact"], (r, summary)
 

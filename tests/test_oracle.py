@@ -226,6 +226,8 @@ def test_full_size_reference_fixture(name):
         r = oracle.evaluator_nms(meta["family"], decoded, hyp, full_nms=True)[0]
         np.testing.assert_array_equal(r.rows, g["rows"][0, :cnt])
         np.testing.assert_array_equal(r.cand_index, g["cand_index"][0])
+    if heads is None:
+        pytest.skip("the CPU generator of this machine does not reproduce the fixture's heads (checksum mismatch)")
     own = oracle.decode_yolov5([h.numpy() for h in heads], num_class=meta["num_class"])
     r = oracle.evaluator_nms(meta["family"], own, hyp)[0]
     np.testing.assert_array_equal(r.cand_index, g["cand_index"][0])

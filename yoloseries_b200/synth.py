@@ -127,6 +127,14 @@ def _logit(p):
     return torch.log(p) - torch.log1p(-p)
 
 
+def _logit64(p):
+    """logit evaluated in float64 and rounded once to float32: vectorised float32 log/exp differ by an ulp between CPU
+    generations (AVX2 vs AVX-512 code paths), float64 results rounded to float32 practically never do -- seed-only
+    fixtures (tests/golden/c1_*) need heads that are bit-identical wherever they are regenerated."""
+    p = p.double().clamp(1e-4, 1 - 1e-4)
+    return (torch.log(p) - torch.log1p(-p)).float()
+
+
 def _crowd_v5(batch, shapes, C, g, device, objects_per_image=700, jitter_px=3.0, jitter_log=0.08, size_lo=16.0,
               size_span=12.0, per_object_score=False):
     """Objects written through the inverse of the v5 decode (trainer/eval_yolov5.py:203-205)."""
@@ -143,8 +151,13 @@ def _crowd_v5(batch, shapes, C, g, device, objects_per_image=700, jitter_px=3.0,
         G = objects_per_image
         cx = torch.rand(G, generator=g, device=device) * (img_w - 64) + 32
         cy = torch.rand(G, generator=g, device=device) * (img_h - 64) + 32
-        bw = torch.exp(torch.rand(G, generator=g, device=device) * math.log(size_span)) * size_lo
-        bh = bw * torch.exp(_randn((G,), g, device, std=0.35))
+        f64 = per_object_score   # deepcrowd: transcendental steps in float64 (see _logit64); 'crowd' keeps its float32 bits
+        if f64:
+            bw = (torch.exp(torch.rand(G, generator=g, device=device).double() * math.log(size_span)) * size_lo).float()
+            bh = (bw.double() * torch.exp(_randn((G,), g, device, std=0.35).double())).float()
+        else:
+            bw = torch.exp(torch.rand(G, generator=g, device=device) * math.log(size_span)) * size_lo
+            bh = bw * torch.exp(_randn((G,), g, device, std=0.35))
         cls_id = torch.randint(0, C, (G,), generator=g, device=device)
         # per_object_score: every object has its own confidence level shared by all its duplicates, so the duplicates of a
         # confident object precede the first candidate of a less confident one in the NMS visiting order
@@ -161,21 +174,35 @@ def _crowd_v5(batch, shapes, C, g, device, objects_per_image=700, jitter_px=3.0,
                         idx = ok.nonzero().flatten()
                         if idx.numel() == 0:
                             continue
+                        # two objects can land in the same cell: an indexed write with duplicate indices is resolved in an
+                        # unspecified order (it depends on the thread count), so keep only the LAST object per cell --
+                        # what a sequential write does -- and the heads are identical wherever they are generated
+                        lin = gy[idx] * w + gx[idx]
+                        order = torch.sort(lin, stable=True).indices
+                        lin_s = lin[order]
+                        last = torch.ones_like(lin_s, dtype=torch.bool)
+                        last[:-1] = lin_s[1:] != lin_s[:-1]
+                        idx = idx[torch.sort(order[last]).values]
                         n = idx.numel()
                         jx = cx[idx] + _randn((n,), g, device, std=jitter_px)
                         jy = cy[idx] + _randn((n,), g, device, std=jitter_px)
-                        jw = bw[idx] * torch.exp(_randn((n,), g, device, std=jitter_log))
-                        jh = bh[idx] * torch.exp(_randn((n,), g, device, std=jitter_log))
+                        if f64:
+                            jw = (bw[idx].double() * torch.exp(_randn((n,), g, device, std=jitter_log).double())).float()
+                            jh = (bh[idx].double() * torch.exp(_randn((n,), g, device, std=jitter_log).double())).float()
+                        else:
+                            jw = bw[idx] * torch.exp(_randn((n,), g, device, std=jitter_log))
+                            jh = bh[idx] * torch.exp(_randn((n,), g, device, std=jitter_log))
                         px = ((jx / s - gx[idx].float()) + 0.5) / 2.0
                         py = ((jy / s - gy[idx].float()) + 0.5) / 2.0
                         pw = torch.sqrt(jw / aw) / 2.0
                         ph = torch.sqrt(jh / ah) / 2.0
                         tgt = heads[lvl][b, a]
                         yy, xx = gy[idx], gx[idx]
-                        tgt[0, yy, xx] = _logit(px)
-                        tgt[1, yy, xx] = _logit(py)
-                        tgt[2, yy, xx] = _logit(pw)
-                        tgt[3, yy, xx] = _logit(ph)
+                        lg = _logit64 if f64 else _logit
+                        tgt[0, yy, xx] = lg(px)
+                        tgt[1, yy, xx] = lg(py)
+                        tgt[2, yy, xx] = lg(pw)
+                        tgt[3, yy, xx] = lg(ph)
                         if per_object_score:
                             tgt[4, yy, xx] = base[idx] + _randn((n,), g, device, std=0.1)
                         else:
