@@ -32,6 +32,7 @@ cudaError_t launch_elementwise_iou(const float *b1, int64_t n1, const float *b2,
 #ifdef YSB_K2_TIMING
 cudaError_t debug_k2_timing(long long *host_out);
 #endif
+void debug_set_nms_threads(int t);
 
 cudaError_t launch_elementwise_iou_backward(const float *b1, int64_t n1, const float *b2, int64_t n2, int kind,
                                             const float *grad_out, float *g1, float *g2, cudaStream_t stream);
@@ -633,6 +634,7 @@ int ysb_elementwise_iou(const float *d_b1, int64_t n1, const float *d_b2, int64_
 
 #ifdef YSB_K2_TIMING
 int ysb_debug_k2_timing(long long *host_out) { return cuda_status(ysb::debug_k2_timing(host_out)); }
+int ysb_debug_set_nms_threads(int t) { ysb::debug_set_nms_threads(t); return YSB_OK; }
 #endif
 
 }  // extern "C"

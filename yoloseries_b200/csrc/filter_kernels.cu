@@ -285,7 +285,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_filter_planes(const __grid_co
 //   * the last C % U class planes and the objectness plane are ONE batch of independent loads (the generic kernel walks
 //     the remainder one dependent load at a time and fetches objectness after the whole class scan).
 // -------------------------------------------------------------------------------------------------------
-template <int U, int THREADS, int MINB>
+__device__ __forceinline__ void prefetch_l2(const float *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// PF > 0: while the loads of batch b are in flight, the lines of batch b + PF are requested into L2 with prefetch
+// instructions (no registers held): the demand loads of later batches then hit L2 instead of waiting a DRAM round trip.
+template <int U, int THREADS, int MINB, int PF = 0>
 __global__ void __launch_bounds__(THREADS, MINB) k_filter_planes_v4(const __grid_constant__ Plan P, uint64_t *__restrict__ keys,
                                                                     int64_t key_cap, int32_t *__restrict__ counts)
 {
@@ -318,10 +322,25 @@ __global__ void __launch_bounds__(THREADS, MINB) k_filter_planes_v4(const __grid
 
         int k = 0;
         uint32_t off = 0;  // k * hw, in elements: an (image, anchor) block is far below 2^32 floats
+        if (PF > 0 && (threadIdx.x & 7) == 0) {
+            // prime the pipeline: batches 1 .. PF (8 lanes share a 128-byte line; one of them asks for it)
+#pragma unroll
+            for (int q = 0; q < PF * U; ++q)
+                if (U + q < C) prefetch_l2(cls + (U + q) * hw);
+        }
         for (; k + U <= C; k += U, off += U * hw) {
             float4 v[U];
 #pragma unroll
             for (int q = 0; q < U; ++q) v[q] = ldg_stream4_256(cls + (off + q * hw));
+            if (PF > 0 && (threadIdx.x & 7) == 0) {
+#pragma unroll
+                for (int q = 0; q < U; ++q) {
+                    const int kk = k + (PF + 1) * U + q;
+                    if (kk < C) prefetch_l2(cls + (off + ((PF + 1) * U + q) * hw));
+                }
+                if (P.use_obj && k == 0)
+                    prefetch_l2((P.obj_src == 2 ? lv.p2 : lv.p0) + (static_cast<size_t>(img * P.A + a) * P.obj_nch + P.obj_ch) * hw + pos);
+            }
 #pragma unroll
             for (int q = 0; q < U; ++q) {
                 top2_update(v[q].x, k + q, m1[0], m2[0], k0[0]);

@@ -7,25 +7,32 @@
 // The reference runs the greedy loop over all M survivors (O(K*M), ~14 s per image at M = 25 k) and truncates to
 // max_det afterwards.  Greedy NMS is prefix-stable, so this kernel visits candidates in the reference's order
 // (score desc, candidate asc) and stops at max_det keeps:
-//   1. radix-select (shared-memory histograms over the normalised 64-bit keys) the next <= 4096 best keys,
-//   2. bitonic-sort them in shared memory, decode their boxes (4 channels each) from the head tensors,
-//   3. walk them in chunks of 64: test each against the kept list (parallel), build the 64x64 in-chunk
-//      suppression bitmask (parallel), resolve the chunk with a bitmask sweep (one warp), append the keeps,
+//   1. pick a score threshold that leaves the next ~500-1000 best keys: radix descent over shared-memory histograms of
+//      the normalised 64-bit keys -- of a strided SAMPLE of them when the image has many survivors (the exact gather
+//      that follows counts what the threshold really selects and falls back to the exact descent if it overflows),
+//   2. gather those keys (one pass over the image's key list), bitonic-sort them (registers + shuffles, shared memory
+//      only for strides >= 32), decode their boxes (4 channels each) from the head tensors as far as the walk gets,
+//   3. walk them 128 at a time: every candidate against the kept list (8 threads per candidate, 4 independent
+//      shared-memory loads in flight each), in-chunk predecessor masks, greedy resolution by one warp, append,
 //   4. if fewer than max_det boxes are kept and candidates remain, select the next tranche and continue,
-//   5. postprocess_bbox count filter / RetinaNet merge / remove_small_boxes, ordered write of the rows.
-// One CTA (1024 threads) per image; images of a batch run concurrently on different SMs.
+//   5. postprocess_bbox count filter / RetinaNet merge (streamed over ALL survivors in blocks, bucketed by class) /
+//      remove_small_boxes, ordered write of the rows -- to the caller's buffer or, in a multi-GPU detection gather, into
+//      every peer's receive slot over NVLink.
+// One CTA per image.  Two flavours of the CTA: 1024 threads (one image per SM: lowest latency, small batches) and 512
+// threads with <= 113 KB of shared memory (two images per SM: the barrier stalls of one overlap the work of the other;
+// batches larger than the SM count).
 #include "ysb_internal.cuh"
 
 namespace ysb {
 
-constexpr int kThreads = 1024;
-constexpr int kTrancheCap = 4096;
-constexpr int kMinTranche = 512;
+constexpr int kTranche = 2048;      // keys selected, sorted and walked at a time
+constexpr int kMinTranche = 512;    // a tranche smaller than this is only taken when nothing else is left
+constexpr int kSampleTarget = 640;  // tranche size aimed at when the threshold comes from a sample
 constexpr int kDigitBits = 11;
 constexpr int kBins = 1 << kDigitBits;
-constexpr int kChunk = 64;
-constexpr int kMaxKeep = YSB_MAX_DET_LIMIT;
-constexpr int kKeyBatch = 8;  // independent 64-bit key loads in flight per thread in the selection passes
+constexpr int kChunk = 128;         // candidates resolved per step of the greedy walk
+constexpr int kChunkWords = kChunk / 32;
+constexpr int kKeyBatch = 8;        // independent 64-bit key loads in flight per thread in the selection passes
 
 // Phase timestamps of image 0..63 (profiling builds only: -DYSB_K2_TIMING), read back by ysb_debug_k2_timing().
 #ifdef YSB_K2_TIMING
@@ -43,30 +50,32 @@ __device__ long long g_k2_timing[64][16];
 #define K2_STAMP(slot) do { } while (0)
 #endif
 
+template <int KEEP>
 struct NmsSmem {
-    uint64_t keys[kTrancheCap];
-    float4 raw[kTrancheCap];
-    uint32_t hist[kBins];
-    float2 kept_x[kMaxKeep];
-    float2 kept_y[kMaxKeep];
-    float kept_a[kMaxKeep];
-    uint64_t kept_key[kMaxKeep];
-    float4 kept_raw[kMaxKeep];
-    uint8_t kept_flag[kMaxKeep];
+    uint64_t keys[kTranche];
+    float4 raw[kTranche];          // raw boxes of the tranche entries; post-filter: offset boxes of a survivor block
+    float area[kTranche];          // post-filter: areas of the offset boxes
+    uint32_t hist[kBins];          // selection histograms; post-filter: class bucket bounds and cursors
+    uint16_t order[kTranche];      // post-filter: survivor indices sorted by class
+    float2 kept_x[KEEP];
+    float2 kept_y[KEEP];
+    float kept_a[KEEP];
+    uint64_t kept_key[KEEP];
+    float4 kept_raw[KEEP];
+    float kept_acc[KEEP][5];       // RetinaNet merge: score-weighted box sums and the weight sum
+    uint16_t kept_cnt[KEEP];       // post-filter: survivors overlapping the kept box by more than the threshold
+    uint8_t kept_flag[KEEP];
     float2 chunk_x[kChunk];
     float2 chunk_y[kChunk];
     float chunk_a[kChunk];
-    uint64_t chunk_mask[kChunk];   // row i: later candidates j > i that i suppresses
-    unsigned int chunk_pred[kChunk][2];  // row i: earlier candidates j < i that suppress i (lo/hi words)
-    float area[kTrancheCap];       // post-filter: areas of the offset boxes
+    uint32_t chunk_pred[kChunk][kChunkWords];  // row j: earlier candidates i < j of the chunk that suppress j
+    uint32_t keep_words[kChunkWords];
     uint8_t chunk_alive[kChunk];
-    uint32_t warp_tmp[kThreads / 32];
-    unsigned long long sel_lo;
-    unsigned long long keep_mask;
+    uint32_t warp_tmp[32];
     int n_sel;
     int sel_digit;
     int sel_above;
-    int out_count;
+    int span_lo, span_hi;
 };
 
 // Arguments of the array flavour (utils.numba_nms / utils.gpu_nms on one explicit box array).
@@ -79,6 +88,7 @@ struct ArrayArgs {
     float thr32;           // torch compares float32 IoUs against the threshold rounded to float32
 };
 
+// One pair test against entry i of a SoA box list (generic: any IoU flavour of the array kernels).
 template <bool ARRAY>
 __device__ __forceinline__ bool pair_hit(const BoxSoA &list, int i, const OffBox &b, const IouThr &t, const ArrayArgs &aa)
 {
@@ -90,49 +100,98 @@ __device__ __forceinline__ bool pair_hit(const BoxSoA &list, int i, const OffBox
     return aa.cmp == YSB_CMP_GT ? (v > aa.thr32) : (v >= aa.thr32);
 }
 
+// The pair test after the x interval of entry i has been loaded and found to overlap b's (numba flavour only).
+template <bool ARRAY>
+__device__ __forceinline__ bool pair_hit_after_x(const BoxSoA &list, int i, float dw, const OffBox &b, const IouThr &t,
+                                                 const ArrayArgs &aa)
+{
+    const float2 ay = list.y[i];
+    const float dh = __fsub_rn(fminf(ay.y, b.y2), fmaxf(ay.x, b.y1));
+    if (!(dh > 0.0f)) return false;
+    const bool strict = ARRAY && aa.cmp == YSB_CMP_GT;
+    return strict ? iou_decide<true>(dw, dh, list.area[i], b.area, t) : iou_decide<false>(dw, dh, list.area[i], b.area, t);
+}
+
+// Does box b hit any of the entries first, first + step, ... < end of the list?  Four independent x-interval loads are
+// in flight per thread; with the 4096-px class offset nearly every pair is rejected by that single 64-bit load.
+template <bool ARRAY>
+__device__ __forceinline__ bool any_hit_strided(const BoxSoA &list, int first, int step, int end, const OffBox &b,
+                                                const IouThr &t, const ArrayArgs &aa)
+{
+    const bool fast = t.positive && (!ARRAY || aa.iou_kind == YSB_IOU_NUMBA_F64MIX);
+    bool hit = false;
+    if (fast) {
+        for (int k0 = first; k0 < end; k0 += 4 * step) {
+            float dw[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = k0 + q * step;
+                const float2 ax = k < end ? list.x[k] : make_float2(0.0f, -1.0f);
+                dw[q] = k < end ? __fsub_rn(fminf(ax.y, b.x2), fmaxf(ax.x, b.x1)) : -1.0f;
+            }
+            // the rare x-overlaps go through ONE copy of the slow path (float64 IoU decision): keeps the loop body small
+            unsigned m = (dw[0] > 0.0f ? 1u : 0u) | (dw[1] > 0.0f ? 2u : 0u) | (dw[2] > 0.0f ? 4u : 0u) | (dw[3] > 0.0f ? 8u : 0u);
+            while (m) {
+                const int q = __ffs(m) - 1;
+                m &= m - 1u;
+                const float d = q == 0 ? dw[0] : (q == 1 ? dw[1] : (q == 2 ? dw[2] : dw[3]));
+                hit |= pair_hit_after_x<ARRAY>(list, k0 + q * step, d, b, t, aa);
+            }
+        }
+    } else {
+        for (int k = first; k < end; k += step) hit |= pair_hit<ARRAY>(list, k, b, t, aa);
+    }
+    return hit;
+}
+
 __device__ __forceinline__ uint64_t norm_key(uint64_t key, uint32_t smin)
 {
     return (static_cast<uint64_t>(static_cast<uint32_t>(key >> 32) - smin) << 32) | (key & 0xffffffffull);
 }
 
-// Block-wide radix descent over the normalised keys: returns a lower bound `lo` such that the set
-// {lo <= nk <= hi_incl} holds at least kMinTranche keys (or everything that is left) and at most kTrancheCap.
-// The smallest such set at the coarsest digit that resolves it is taken: the NMS walk usually ends long before a
-// tranche is exhausted, so sorting more than it needs is wasted work.
-__device__ uint64_t select_lower_bound(NmsSmem &S, const uint64_t *__restrict__ keys, int M, uint32_t smin,
-                                       uint64_t hi_incl, int nbits)
+// Block-wide radix descent over the normalised keys nk <= hi_incl, visiting every `stride`-th key of the list: returns
+// a lower bound `lo` such that {lo <= nk <= hi_incl} holds -- by the (sampled) counts -- at least `want` keys, or
+// everything that is left, and at most `cap`.  The smallest such set at the coarsest digit that resolves it is taken.
+// stride == 1: exact counts.  stride > 1: an estimate; the caller's exact gather pass validates it.
+template <int THREADS, int KEEP>
+__device__ uint64_t select_lower_bound(NmsSmem<KEEP> &S, const uint64_t *__restrict__ keys, int M, uint32_t smin,
+                                       uint64_t hi_incl, int nbits, int stride, int want, int cap)
 {
     const int tid = threadIdx.x;
     int sh = nbits > kDigitBits ? nbits - kDigitBits : 0;  // shift of the current digit
     int width = nbits - sh;                                // bits in the current digit
     uint64_t prefix = 0;                                   // value of nk >> (sh + width) along the descent path
     bool have_prefix = false;
-    int acc = 0;                                           // keys already covered above the path
+    int acc = 0;                                           // (sampled) keys already covered above the path
+    const int ms = (M + stride - 1) / stride;              // sample size
     for (;;) {
-        for (int i = tid; i < kBins; i += kThreads) S.hist[i] = 0;
+        for (int i = tid; i < kBins; i += THREADS) S.hist[i] = 0;
         if (tid == 0) { S.sel_digit = -1; S.n_sel = 0; S.sel_above = 0; }
         __syncthreads();
         const int top = sh + width;
         const uint32_t dmask = (1u << width) - 1u;
-        for (int i0 = 0; i0 < M; i0 += kKeyBatch * kThreads) {
+        for (int i0 = 0; i0 < ms; i0 += kKeyBatch * THREADS) {
             uint64_t kk[kKeyBatch];
 #pragma unroll
             for (int q = 0; q < kKeyBatch; ++q) {
-                const int i = i0 + q * kThreads + tid;
-                kk[q] = i < M ? __ldg(keys + i) : 0ull;
+                const int i = i0 + q * THREADS + tid;
+                kk[q] = i < ms ? __ldg(keys + static_cast<int64_t>(i) * stride) : 0ull;
             }
 #pragma unroll
             for (int q = 0; q < kKeyBatch; ++q) {
-                if (i0 + q * kThreads + tid >= M) continue;
+                if (i0 + q * THREADS + tid >= ms) continue;
                 const uint64_t nk = norm_key(kk[q], smin);
                 if (nk <= hi_incl && (!have_prefix || (nk >> top) == prefix))
                     atomicAdd(&S.hist[static_cast<uint32_t>(nk >> sh) & dmask], 1u);
             }
         }
         __syncthreads();
-        // suffix sums S(d) = #keys with digit >= d; thread t owns digits 2t, 2t+1
-        const uint32_t h0 = S.hist[2 * tid], h1 = S.hist[2 * tid + 1];
-        const uint32_t part = h0 + h1;
+        // suffix sums S(d) = #keys with digit >= d; thread t owns digits PER*t .. PER*t + PER - 1
+        constexpr int PER = kBins / THREADS;
+        uint32_t h[PER];
+        uint32_t part = 0;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) { h[q] = S.hist[PER * tid + q]; part += h[q]; }
         uint32_t incl = part;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -142,20 +201,22 @@ __device__ uint64_t select_lower_bound(NmsSmem &S, const uint64_t *__restrict__ 
         if ((tid & 31) == 0) S.warp_tmp[tid >> 5] = incl;
         __syncthreads();
         uint32_t above = 0;
-        for (int w = (tid >> 5) + 1; w < kThreads / 32; ++w) above += S.warp_tmp[w];
-        const uint32_t s_hi = incl - part + above;  // S(2t+2)
-        const uint32_t s1 = s_hi + h1;              // S(2t+1)
-        const uint32_t s0 = s1 + h0;                // S(2t)
-        const uint32_t need = static_cast<uint32_t>(kMinTranche > acc ? kMinTranche - acc : 0);
+        for (int w = (tid >> 5) + 1; w < THREADS / 32; ++w) above += S.warp_tmp[w];
+        uint32_t s_hi = incl - part + above;  // S(PER*t + PER)
+        const uint32_t need = static_cast<uint32_t>(want > acc ? want - acc : 0);
         // d_a = largest digit with S(d_a) >= need
-        if (s1 >= need && s_hi < need) { S.sel_digit = 2 * tid + 1; S.n_sel = static_cast<int>(s1); S.sel_above = static_cast<int>(s_hi); }
-        else if (s0 >= need && s1 < need) { S.sel_digit = 2 * tid; S.n_sel = static_cast<int>(s0); S.sel_above = static_cast<int>(s1); }
+#pragma unroll
+        for (int q = PER - 1; q >= 0; --q) {
+            const uint32_t s_lo = s_hi + h[q];  // S(PER*t + q)
+            if (s_lo >= need && s_hi < need) { S.sel_digit = PER * tid + q; S.n_sel = static_cast<int>(s_lo); S.sel_above = static_cast<int>(s_hi); }
+            s_hi = s_lo;
+        }
         __syncthreads();
         const int da = S.sel_digit, covered = acc + S.n_sel, abv = acc + S.sel_above;
         __syncthreads();
         const uint64_t base = have_prefix ? (prefix << top) : 0ull;
-        if (da < 0) return base;  // fewer than kMinTranche keys under this prefix: take them all
-        if (covered <= kTrancheCap || sh == 0) return base | (static_cast<uint64_t>(da) << sh);
+        if (da < 0) return base;  // fewer than `want` keys under this prefix: take them all
+        if (covered <= cap || sh == 0) return base | (static_cast<uint64_t>(da) << sh);
         // digit d_a alone overflows the tranche: refine inside it
         prefix = (have_prefix ? (prefix << width) : 0ull) | static_cast<uint64_t>(da);
         have_prefix = true;
@@ -166,45 +227,51 @@ __device__ uint64_t select_lower_bound(NmsSmem &S, const uint64_t *__restrict__ 
     }
 }
 
-// Descending sort of keys[0..n) (n <= 1024*E) by a bitonic network held in registers: element i = tid + 1024*r lives in
-// register r of thread tid.  Strides >= 1024 are thread-local, strides < 32 use warp shuffles, only strides 32..512 go
-// through shared memory (15 of the 55 stages at n = 1024).  Slots beyond n sort as 0 (smaller than any real key).
-template <int E>
+// Descending sort of keys[0..n) (n <= THREADS*E) by a bitonic network held in registers: element i = tid + THREADS*r
+// lives in register r of thread tid.  Strides >= THREADS are thread-local, strides < 32 use warp shuffles, only strides
+// 32..THREADS/2 go through shared memory.  Slots beyond n sort as 0 (smaller than any real key).
+template <int THREADS, int E, int DR>
+__device__ __forceinline__ void local_stage(uint64_t (&v)[E], int tid, int k)
+{
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        if ((r & DR) == 0 && r + DR < E) {
+            const bool desc = ((tid + THREADS * r) & k) == 0;
+            uint64_t &a = v[r], &b = v[(r + DR) % E];
+            const uint64_t hi = a > b ? a : b, lo = a > b ? b : a;
+            a = desc ? hi : lo;
+            b = desc ? lo : hi;
+        }
+    }
+}
+
+template <int THREADS, int E>
 __device__ void bitonic_sort_desc(uint64_t *keys, int n)
 {
     const int tid = threadIdx.x;
-    constexpr int n2 = kThreads * E;
+    constexpr int n2 = THREADS * E;
     uint64_t v[E];
 #pragma unroll
     for (int r = 0; r < E; ++r) {
-        const int i = tid + kThreads * r;
+        const int i = tid + THREADS * r;
         v[r] = i < n ? keys[i] : 0ull;
     }
     __syncthreads();
     for (int k = 2; k <= n2; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j >= kThreads) {
-                // thread-local stage: register pairs (0,1),(2,3) for stride 1024, (0,2),(1,3) for stride 2048
-                auto cx = [&](int r0, uint64_t &a, uint64_t &b) {
-                    const bool desc = ((tid + kThreads * r0) & k) == 0;
-                    const uint64_t hi = a > b ? a : b, lo = a > b ? b : a;
-                    a = desc ? hi : lo;
-                    b = desc ? lo : hi;
-                };
-                if (E >= 2 && j == kThreads) {
-                    cx(0, v[0], v[1 % E]);
-                    if (E == 4) cx(2, v[2 % E], v[3 % E]);
-                } else if (E == 4 && j == 2 * kThreads) {
-                    cx(0, v[0], v[2 % E]);
-                    cx(1, v[1 % E], v[3 % E]);
-                }
+            if (j >= THREADS) {
+                // thread-local stage: register pairs (r, r + j/THREADS); the pair distance is resolved at compile time so
+                // that v[] stays in registers
+                if (j == THREADS) local_stage<THREADS, E, 1>(v, tid, k);
+                else if (j == 2 * THREADS) local_stage<THREADS, E, 2>(v, tid, k);
+                else local_stage<THREADS, E, 4>(v, tid, k);
             } else if (j >= 32) {
 #pragma unroll
-                for (int r = 0; r < E; ++r) keys[tid + kThreads * r] = v[r];
+                for (int r = 0; r < E; ++r) keys[tid + THREADS * r] = v[r];
                 __syncthreads();
 #pragma unroll
                 for (int r = 0; r < E; ++r) {
-                    const int i = tid + kThreads * r;
+                    const int i = tid + THREADS * r;
                     const uint64_t o = keys[i ^ j];
                     const bool take_max = ((i & j) == 0) == ((i & k) == 0);
                     v[r] = take_max ? (v[r] > o ? v[r] : o) : (v[r] > o ? o : v[r]);
@@ -213,7 +280,7 @@ __device__ void bitonic_sort_desc(uint64_t *keys, int n)
             } else {
 #pragma unroll
                 for (int r = 0; r < E; ++r) {
-                    const int i = tid + kThreads * r;
+                    const int i = tid + THREADS * r;
                     const uint64_t o = __shfl_xor_sync(0xffffffffu, v[r], j);
                     const bool take_max = ((i & j) == 0) == ((i & k) == 0);
                     v[r] = take_max ? (v[r] > o ? v[r] : o) : (v[r] > o ? o : v[r]);
@@ -222,8 +289,16 @@ __device__ void bitonic_sort_desc(uint64_t *keys, int n)
         }
     }
 #pragma unroll
-    for (int r = 0; r < E; ++r) keys[tid + kThreads * r] = v[r];
+    for (int r = 0; r < E; ++r) keys[tid + THREADS * r] = v[r];
     __syncthreads();
+}
+
+template <int THREADS>
+__device__ __forceinline__ void sort_tranche(uint64_t *keys, int n)
+{
+    if (n <= THREADS) bitonic_sort_desc<THREADS, 1>(keys, n);
+    else if (n <= 2 * THREADS) bitonic_sort_desc<THREADS, 2>(keys, n);
+    else bitonic_sort_desc<THREADS, kTranche / THREADS>(keys, n);
 }
 
 // order-preserving float <-> int maps (signed integer compare == float compare; used for shared-memory atomicMin/Max)
@@ -247,17 +322,59 @@ __device__ __forceinline__ const Plan &pass_of(const Plan &P, const ExtraPasses 
     return X.p[sel];
 }
 
+// Raw boxes of the tranche entries [from, upto) into S.raw.  YOLOv8 raw heads: a box is 4 sides x 16 DFL bins = 64
+// scattered loads; one thread per (candidate, side) keeps its 16 bin loads in flight together and runs the softmax
+// expectation in registers (the decode kernel's bin order), the four sides of a candidate meet by shuffle -- THREADS/4
+// boxes per DRAM round trip.  Every other layout: one thread per box.
+template <bool ARRAY, typename EXTRA, int THREADS, int KEEP>
+__device__ __forceinline__ void decode_boxes(NmsSmem<KEEP> &S, const Plan &P, const EXTRA &X, const ArrayArgs &aa, int img,
+                                             int from, int upto)
+{
+    const int tid = threadIdx.x;
+    if (!ARRAY && P.family == YSB_YOLOV8 && P.input_kind == YSB_INPUT_RAW_HEADS) {
+        for (int i0 = from; i0 < upto; i0 += THREADS / 4) {
+            const int i = i0 + (tid >> 2), side = tid & 3;
+            float sv = 0.0f;
+            const bool ok = i < upto;
+            if (ok) {
+                int cand = static_cast<int>(key_cand(S.keys[i]));
+                const Plan &Q = pass_of(P, X, cand);
+                sv = v8_side_value(Q, img, cand, side);
+            }
+            const unsigned qb = (tid & 31) & ~3u;
+            const float s0 = __shfl_sync(0xffffffffu, sv, qb), s1 = __shfl_sync(0xffffffffu, sv, qb + 1);
+            const float s2 = __shfl_sync(0xffffffffu, sv, qb + 2), s3 = __shfl_sync(0xffffffffu, sv, qb + 3);
+            if (ok && side == 0) {
+                int c2 = static_cast<int>(key_cand(S.keys[i]));
+                const Plan &Q = pass_of(P, X, c2);
+                S.raw[i] = tta_undo(Q, v8_box_from_sides(Q, c2, s0, s1, s2, s3));
+            }
+        }
+    } else {
+        for (int i = from + tid; i < upto; i += THREADS) {
+            int cand = static_cast<int>(key_cand(S.keys[i]));
+            if (ARRAY) {
+                S.raw[i] = __ldg(aa.boxes + cand);
+            } else {
+                const Plan &Q = pass_of(P, X, cand);
+                S.raw[i] = candidate_xyxy(Q, img, cand);
+            }
+        }
+    }
+}
+
 // EXTRA = NoExtraPasses (one set of heads) or ExtraPasses (TTA: boxes are decoded from the pass a candidate came from;
 // thresholds / NMS settings are those of P, identical in every pass).
-template <bool ARRAY, typename EXTRA>
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool ARRAY, typename EXTRA, int THREADS, int KEEP>
+__global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2)
 k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, const uint64_t *__restrict__ keys_all,
              int64_t key_cap, const int32_t *__restrict__ counts, float *__restrict__ dets,
              int32_t *__restrict__ det_idx, int32_t *__restrict__ det_cnt, const ArrayArgs aa,
              const __grid_constant__ GatherSink G)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    NmsSmem &S = *reinterpret_cast<NmsSmem *>(smem_raw);
+    using Smem = NmsSmem<KEEP>;
+    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x;
     const int img = blockIdx.x;
     const int32_t *cnt = counts + img * 4;
@@ -285,226 +402,235 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
     const IouThr thr = make_iou_thr(P.iou_thr);
     const int max_det = P.max_det;
     // postprocess_bbox runs only for 1 < M < 3000 (FCOS: <= 300), trainer/eval_yolov5.py:306-307
-    const bool window = !ARRAY && P.postprocess_bbox && M > 1 && M < P.window_hi && M <= kTrancheCap;
+    const bool window = !ARRAY && P.postprocess_bbox && M > 1 && M < P.window_hi;
 
-    int kept = 0, processed = 0, n_tranche = 0;
+    int kept = 0, processed = 0, n_tranche = 0, decoded_upto = 0;
     uint64_t hi_incl = ~0ull;
     for (;;) {
         K2_STAMP(0);
         K2_ACC_RESET();
-        // ---- 1. select the next tranche ------------------------------------------------------------------
+        // ---- 1. threshold of the next tranche ---------------------------------------------------------------
+        // Many survivors left: estimate it from every stride-th key (the list is in arrival order, i.e. unordered in
+        // score), aiming above the minimum so that sampling noise rarely leaves the tranche short.
         uint64_t lo = 0;
-        if (M - processed > kTrancheCap) lo = select_lower_bound(S, keys, M, smin, hi_incl, nbits);
-        K2_STAMP(1);
-        if (tid == 0) S.n_sel = 0;
-        __syncthreads();
-        for (int i0 = 0; i0 < M; i0 += kKeyBatch * kThreads) {
-            uint64_t kk[kKeyBatch];
-#pragma unroll
-            for (int q = 0; q < kKeyBatch; ++q) {
-                const int i = i0 + q * kThreads + tid;
-                kk[q] = i < M ? __ldg(keys + i) : 0ull;
+        int n = 0;
+        const int remaining = M - processed;
+        int stride = remaining > 4 * kTranche ? (remaining >= 32 * kTranche ? 32 : remaining / kTranche) : 1;
+        for (;;) {
+            if (remaining > kTranche) {
+                const int want = stride > 1 ? (kSampleTarget + stride - 1) / stride : kMinTranche;
+                const int cap = stride > 1 ? (kTranche * 3 / 4) / stride : kTranche;
+                lo = select_lower_bound<THREADS, KEEP>(S, keys, M, smin, hi_incl, nbits, stride, want, cap);
             }
+            K2_STAMP(1);
+            if (tid == 0) S.n_sel = 0;
+            __syncthreads();
+            // ---- gather {lo <= nk <= hi_incl}: one exact pass over the key list -----------------------------------
+            for (int i0 = 0; i0 < M; i0 += kKeyBatch * THREADS) {
+                uint64_t kk[kKeyBatch];
 #pragma unroll
-            for (int q = 0; q < kKeyBatch; ++q) {
-                const uint64_t nk = norm_key(kk[q], smin);
-                const bool in = (i0 + q * kThreads + tid < M) && nk >= lo && nk <= hi_incl;
-                const unsigned bal = __ballot_sync(0xffffffffu, in);
-                if (bal) {
-                    int base = 0;
-                    if ((tid & 31) == 0) base = atomicAdd(&S.n_sel, __popc(bal));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (in) {
-                        const int at = base + __popc(bal & ((1u << (tid & 31)) - 1u));
-                        if (at < kTrancheCap) S.keys[at] = kk[q];
+                for (int q = 0; q < kKeyBatch; ++q) {
+                    const int i = i0 + q * THREADS + tid;
+                    kk[q] = i < M ? __ldg(keys + i) : 0ull;
+                }
+#pragma unroll
+                for (int q = 0; q < kKeyBatch; ++q) {
+                    const uint64_t nk = norm_key(kk[q], smin);
+                    const bool in = (i0 + q * THREADS + tid < M) && nk >= lo && nk <= hi_incl;
+                    const unsigned bal = __ballot_sync(0xffffffffu, in);
+                    if (bal) {
+                        int base = 0;
+                        if ((tid & 31) == 0) base = atomicAdd(&S.n_sel, __popc(bal));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (in) {
+                            const int at = base + __popc(bal & ((1u << (tid & 31)) - 1u));
+                            if (at < kTranche) S.keys[at] = kk[q];
+                        }
                     }
                 }
             }
+            __syncthreads();
+            n = S.n_sel;
+            __syncthreads();
+            if (n <= kTranche) break;
+            stride = 1;  // the sampled threshold let too many keys through: redo with exact counts
         }
-        __syncthreads();
         K2_STAMP(2);
-        const int n = min(S.n_sel, kTrancheCap);
         n_tranche = n;
-        // ---- 2. sort descending, decode boxes -------------------------------------------------------------
-        if (n <= kThreads) bitonic_sort_desc<1>(S.keys, n);
-        else if (n <= 2 * kThreads) bitonic_sort_desc<2>(S.keys, n);
-        else bitonic_sort_desc<4>(S.keys, n);
+        // ---- 2. sort descending -----------------------------------------------------------------------------------
+        sort_tranche<THREADS>(S.keys, n);
         const int n_use = min(n, limit - processed);
         K2_STAMP(3);
-        int decoded_upto = 0;  // boxes are decoded 1024 at a time, only as far as the NMS walk gets
-        // ---- 3. greedy NMS over the tranche, 64 candidates at a time ---------------------------------------
+        decoded_upto = 0;  // boxes are decoded a batch at a time, only as far as the NMS walk gets
+        // ---- 3. greedy NMS over the tranche, kChunk candidates at a time ------------------------------------------
+        constexpr int TPC = THREADS / kChunk;  // threads per candidate
         for (int c0 = 0; c0 < n_use && kept < max_det; c0 += kChunk) {
             const int cn = min(kChunk, n_use - c0);
             K2_ACC_BEGIN();
             if (c0 + cn > decoded_upto) {
-                if (!ARRAY && P.family == YSB_YOLOV8 && P.input_kind == YSB_INPUT_RAW_HEADS && P.dfl_bins <= 16) {
-                    // DFL decode of exactly this chunk.  A box needs 4 sides x 16 bins = 64 scattered loads: (i) sixteen
-                    // threads per candidate fetch 4 bin logits each (all independent, one round trip) into shared memory
-                    // laid out [bin][candidate*4 + side]; (ii) one thread per (candidate, side) runs the softmax
-                    // expectation from shared memory (conflict-free: consecutive threads, consecutive words) in the
-                    // same bin order as the decode kernel; (iii) the four sides of a candidate meet by shuffle.
-                    float *dfl = S.area;  // 16 x 256 floats; the areas are only used by the post-filter, after this loop
-                    {
-                        const int j = tid >> 4, part = tid & 15, side = part >> 2, b0 = (part & 3) << 2;
-                        if (j < cn) {
-                            int cand = static_cast<int>(key_cand(S.keys[c0 + j]));
-                            const Plan &Q = pass_of(P, X, cand);
-                            const LevelDesc &lv = Q.lv[find_level(Q, cand)];
-                            const float *q = lv.p0 + (static_cast<size_t>(img) * Q.cls_nch + static_cast<size_t>(side) * Q.dfl_bins) * lv.hw +
-                                             (cand - lv.cand_off);
-                            float v[4];
-#pragma unroll
-                            for (int b = 0; b < 4; ++b)
-                                v[b] = (b0 + b) < Q.dfl_bins ? __ldg(q + static_cast<size_t>(b0 + b) * lv.hw) : -INFINITY;
-#pragma unroll
-                            for (int b = 0; b < 4; ++b) dfl[(b0 + b) * 256 + j * 4 + side] = v[b];
-                        }
-                    }
-                    __syncthreads();
-                    if (tid < 256) {
-                        const int j = tid >> 2, side = tid & 3;
-                        float sv = 0.0f;
-                        if (j < cn) {
-                            float v[16];
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] = dfl[i * 256 + tid];
-                            sv = v8_side_from_bins(v, P.dfl_bins);
-                        }
-                        const unsigned qb = (tid & 31) & ~3u;
-                        const float s0 = __shfl_sync(0xffffffffu, sv, qb), s1 = __shfl_sync(0xffffffffu, sv, qb + 1);
-                        const float s2 = __shfl_sync(0xffffffffu, sv, qb + 2), s3 = __shfl_sync(0xffffffffu, sv, qb + 3);
-                        if (side == 0 && j < cn) {
-                            int cand = static_cast<int>(key_cand(S.keys[c0 + j]));
-                            const Plan &Q = pass_of(P, X, cand);
-                            S.raw[c0 + j] = tta_undo(Q, v8_box_from_sides(Q, cand, s0, s1, s2, s3));
-                        }
-                    }
-                    decoded_upto = c0 + cn;
-                } else {
-                    const int i = decoded_upto + tid;
-                    if (i < n_use) {
-                        int cand = static_cast<int>(key_cand(S.keys[i]));
-                        if (ARRAY) {
-                            S.raw[i] = __ldg(aa.boxes + cand);
-                        } else {
-                            const Plan &Q = pass_of(P, X, cand);
-                            S.raw[i] = candidate_xyxy(Q, img, cand);
-                        }
-                    }
-                    decoded_upto = min(n_use, decoded_upto + kThreads);
-                }
+                // one batch = one DRAM round trip; a YOLOv8 box costs 64 loads + 4 softmax expectations, so only as many as
+                // one round of (candidate, side) threads covers are decoded ahead of the walk
+                const bool dfl = !ARRAY && P.family == YSB_YOLOV8 && P.input_kind == YSB_INPUT_RAW_HEADS;
+                const int upto = min(n_use, decoded_upto + (dfl ? max(THREADS / 4, kChunk) : THREADS));
+                decode_boxes<ARRAY, EXTRA, THREADS, KEEP>(S, P, X, aa, img, decoded_upto, upto);
+                decoded_upto = upto;
                 __syncthreads();
             }
             K2_ACC(8);
-            // phase A: 16 threads per candidate test it against the kept list
+            const int j = tid / TPC, sub = tid % TPC;
+            const unsigned group = ((1u << TPC) - 1u) << ((tid & 31) / TPC * TPC);
+            // phase A: TPC threads per candidate test it against the kept list
             {
-                const int j = tid >> 4, sub = tid & 15;
                 bool sup = false;
-                OffBox ob;
-                bool valid = j < cn;
+                OffBox ob{};
+                const bool valid = j < cn;
                 float score = 0.f;
                 if (valid) {
                     const uint64_t key = S.keys[c0 + j];
                     score = key_score(key);
                     const float off = P.class_aware ? __fmul_rn(static_cast<float>(key_cls(key)), 4096.0f) : 0.0f;
                     ob = make_offbox(S.raw[c0 + j], off);
-                    for (int k = sub; k < kept; k += 16) sup |= pair_hit<ARRAY>(kept_box, k, ob, thr, aa);
+                    sup = any_hit_strided<ARRAY>(kept_box, sub, TPC, kept, ob, thr, aa);
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, sup);
-                const unsigned half = (tid & 16) ? 0xffff0000u : 0x0000ffffu;
-                if (sub == 0 && j < kChunk) {
-                    S.chunk_pred[j][0] = 0u;
-                    S.chunk_pred[j][1] = 0u;
+                if (sub == 0) {
                     // a zero score is never picked by "while sum > 0" (utils/nms.py:16): it is neither kept nor a suppressor
-                    S.chunk_alive[j] = valid && !(bal & half) && score > 0.0f;
+                    S.chunk_alive[j] = valid && !(bal & group) && score > 0.0f;
                     if (valid) soa_store(chunk_box, j, ob);
                 }
             }
             __syncthreads();
             K2_ACC(9);
-            // phase B: in-chunk suppression bitmask, mask[i] bit j (j > i) = IoU(i, j) reaches the threshold
+            // phase B: in-chunk predecessor masks, pred[j] bit i (i < j) = IoU(i, j) reaches the threshold, both alive
+            bool conflict;
             {
-                const int i = tid >> 4, sub = tid & 15;
-                uint32_t lo32 = 0, hi32 = 0;
-                if (i < cn && S.chunk_alive[i]) {
-                    const OffBox bi = soa_load(chunk_box, i);
+                uint32_t w[kChunkWords];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int j = q * 16 + sub;  // lanes walk consecutive boxes: conflict-free shared loads
-                        if (j > i && j < cn && S.chunk_alive[j] && pair_hit<ARRAY>(chunk_box, j, bi, thr, aa)) {
-                            if (j < 32) lo32 |= 1u << j; else hi32 |= 1u << (j - 32);
-                            atomicOr(&S.chunk_pred[j][i >> 5], 1u << (i & 31));  // rare: suppression inside a chunk
+                for (int c = 0; c < kChunkWords; ++c) w[c] = 0u;
+                if (j < cn && S.chunk_alive[j]) {
+                    const OffBox bj = soa_load(chunk_box, j);
+                    const bool fast = thr.positive && (!ARRAY || aa.iou_kind == YSB_IOU_NUMBA_F64MIX);
+                    for (int i0 = sub; i0 < j; i0 += 4 * TPC) {
+                        float dw[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int i = i0 + q * TPC;
+                            const float2 ax = i < j ? chunk_box.x[i] : make_float2(0.0f, -1.0f);
+                            dw[q] = i < j ? __fsub_rn(fminf(ax.y, bj.x2), fmaxf(ax.x, bj.x1)) : -1.0f;
+                        }
+                        unsigned m = 0u;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (i0 + q * TPC < j && (!fast || dw[q] > 0.0f)) m |= 1u << q;
+                        while (m) {   // rare: ONE copy of the slow path
+                            const int q = __ffs(m) - 1;
+                            m &= m - 1u;
+                            const int i = i0 + q * TPC;
+                            if (!S.chunk_alive[i]) continue;
+                            const float d = q == 0 ? dw[0] : (q == 1 ? dw[1] : (q == 2 ? dw[2] : dw[3]));
+                            const bool hit = fast ? pair_hit_after_x<ARRAY>(chunk_box, i, d, bj, thr, aa)
+                                                  : pair_hit<ARRAY>(chunk_box, i, bj, thr, aa);
+                            if (hit) {
+#pragma unroll
+                                for (int c = 0; c < kChunkWords; ++c)   // (static register index: no local memory)
+                                    w[c] |= (i >> 5) == c ? 1u << (i & 31) : 0u;
+                            }
                         }
                     }
                 }
-                const unsigned half = (tid & 16) ? 0xffff0000u : 0x0000ffffu;
-                lo32 = __reduce_or_sync(half, lo32);
-                hi32 = __reduce_or_sync(half, hi32);
-                if (sub == 0) S.chunk_mask[i] = (static_cast<uint64_t>(hi32) << 32) | lo32;
+                // OR the TPC partial masks of a candidate (xor-shuffles stay inside the aligned group of TPC lanes); hits
+                // are rare, so most warps skip it
+                if (__any_sync(0xffffffffu, (w[0] | w[1] | w[2] | w[3]) != 0u)) {
+#pragma unroll
+                    for (int c = 0; c < kChunkWords; ++c)
+#pragma unroll
+                        for (int d = 1; d < TPC; d <<= 1) w[c] |= __shfl_xor_sync(0xffffffffu, w[c], d);
+                }
+                uint32_t any_w = 0u;
+#pragma unroll
+                for (int c = 0; c < kChunkWords; ++c) {
+                    if (sub == 0) S.chunk_pred[j][c] = w[c];
+                    any_w |= w[c];
+                }
+                // the barrier that ends the phase also tells everybody whether the chunk has any in-chunk suppression
+                conflict = __syncthreads_or(any_w != 0u) != 0;
             }
-            __syncthreads();
             K2_ACC(10);
-            // phase C: resolve the chunk (warp 0)
-            if (tid < 32) {
-                const unsigned a_lo = __ballot_sync(0xffffffffu, S.chunk_alive[tid] != 0);
-                const unsigned a_hi = __ballot_sync(0xffffffffu, S.chunk_alive[tid + 32] != 0);
-                const uint64_t alive = (static_cast<uint64_t>(a_hi) << 32) | a_lo;
-                const bool conflict = (((alive >> tid) & 1ull) && (S.chunk_mask[tid] & alive)) ||
-                                      (((alive >> (tid + 32)) & 1ull) && (S.chunk_mask[tid + 32] & alive));
-                const unsigned any = __ballot_sync(0xffffffffu, conflict);
-                uint64_t keep = alive;
-                if (any) {
-                    // Greedy resolution without a serial walk: a candidate is decided as soon as all of its earlier
-                    // in-chunk suppressors are decided -- kept if none of them was kept, dropped otherwise.  The
-                    // lowest undecided candidate is always decidable, so this ends; typical chunks need 2-4 rounds.
-                    const uint64_t p0 = (static_cast<uint64_t>(S.chunk_pred[tid][1]) << 32 | S.chunk_pred[tid][0]) & alive;
-                    const uint64_t p1 = (static_cast<uint64_t>(S.chunk_pred[tid + 32][1]) << 32 | S.chunk_pred[tid + 32][0]) & alive;
-                    uint64_t U = alive, K = 0;
-                    while (U) {
-                        const bool in0 = (U >> tid) & 1ull, in1 = (U >> (tid + 32)) & 1ull;
-                        const bool sup0 = in0 && (p0 & K), sup1 = in1 && (p1 & K);
-                        const bool kp0 = in0 && !(p0 & K) && !(p0 & U), kp1 = in1 && !(p1 & K) && !(p1 & U);
-                        const uint64_t Rk = (static_cast<uint64_t>(__ballot_sync(0xffffffffu, kp1)) << 32) | __ballot_sync(0xffffffffu, kp0);
-                        const uint64_t Rs = (static_cast<uint64_t>(__ballot_sync(0xffffffffu, sup1)) << 32) | __ballot_sync(0xffffffffu, sup0);
-                        K |= Rk;
-                        U &= ~(Rk | Rs);
+            // phase C: who is kept.  No in-chunk suppression (the common case): every alive candidate.  Otherwise warp 0
+            // resolves the chunk; lane l owns candidates l, l + 32, l + 64, l + 96.
+            if (!conflict) {
+                if (tid < kChunk) {
+                    const unsigned a = __ballot_sync(0xffffffffu, S.chunk_alive[tid] != 0);
+                    if ((tid & 31) == 0) S.keep_words[tid >> 5] = a;
+                }
+            } else if (tid < 32) {
+                uint32_t alive[kChunkWords], p[kChunkWords][kChunkWords];
+#pragma unroll
+                for (int c = 0; c < kChunkWords; ++c) alive[c] = __ballot_sync(0xffffffffu, S.chunk_alive[tid + 32 * c] != 0);
+#pragma unroll
+                for (int c = 0; c < kChunkWords; ++c)
+#pragma unroll
+                    for (int q = 0; q < kChunkWords; ++q)
+                        p[c][q] = q <= c ? (S.chunk_pred[tid + 32 * c][q] & alive[q]) : 0u;
+                // Greedy resolution without a serial walk: a candidate is decided as soon as all of its earlier
+                // in-chunk suppressors are decided -- kept if none of them was kept, dropped otherwise.  The
+                // lowest undecided candidate is always decidable, so this ends; typical chunks need 2-4 rounds.
+                uint32_t U[kChunkWords], K[kChunkWords];
+#pragma unroll
+                for (int c = 0; c < kChunkWords; ++c) { U[c] = alive[c]; K[c] = 0u; }
+                for (;;) {
+                    uint32_t any_u = 0u;
+#pragma unroll
+                    for (int c = 0; c < kChunkWords; ++c) any_u |= U[c];
+                    if (!any_u) break;
+                    uint32_t Rk[kChunkWords], Rs[kChunkWords];
+#pragma unroll
+                    for (int c = 0; c < kChunkWords; ++c) {
+                        const bool in = (U[c] >> tid) & 1u;
+                        uint32_t hk = 0u, hu = 0u;
+#pragma unroll
+                        for (int q = 0; q < kChunkWords; ++q) { hk |= p[c][q] & K[q]; hu |= p[c][q] & U[q]; }
+                        Rk[c] = __ballot_sync(0xffffffffu, in && !hk && !hu);
+                        Rs[c] = __ballot_sync(0xffffffffu, in && hk);
                     }
-                    keep = K;
+#pragma unroll
+                    for (int c = 0; c < kChunkWords; ++c) { K[c] |= Rk[c]; U[c] &= ~(Rk[c] | Rs[c]); }
                 }
                 if (tid == 0) {
-                    const int room = max_det - kept;
-                    int cntk = __popcll(keep);
-                    while (cntk > room) {  // drop the lowest-priority (highest index) keeps beyond max_det
-                        keep &= ~(1ull << (63 - __clzll(static_cast<long long>(keep))));
-                        --cntk;
-                    }
-                    S.keep_mask = keep;
+#pragma unroll
+                    for (int c = 0; c < kChunkWords; ++c) S.keep_words[c] = K[c];
                 }
             }
             __syncthreads();
             K2_ACC(11);
-            const uint64_t keep = S.keep_mask;
-            if (tid < kChunk && ((keep >> tid) & 1ull)) {
-                const int at = kept + __popcll(keep & ((1ull << tid) - 1ull));
-                soa_store(kept_box, at, soa_load(chunk_box, tid));
-                if (ARRAY) {
-                    aa.keep[at] = static_cast<int32_t>(key_cand(S.keys[c0 + tid]));
-                } else {
-                    S.kept_key[at] = S.keys[c0 + tid];
-                    S.kept_raw[at] = S.raw[c0 + tid];
+            // append the keeps in order; keeps beyond max_det (the lowest-priority ones of the chunk) are dropped
+            int added = 0;
+            {
+                uint32_t kw[kChunkWords];
+#pragma unroll
+                for (int c = 0; c < kChunkWords; ++c) { kw[c] = S.keep_words[c]; added += __popc(kw[c]); }
+                added = min(added, max_det - kept);
+                if (tid < kChunk) {
+                    const uint32_t mine = S.keep_words[tid >> 5];
+                    int before = __popc(mine & ((1u << (tid & 31)) - 1u));
+#pragma unroll
+                    for (int c = 0; c < kChunkWords; ++c)
+                        if (c < (tid >> 5)) before += __popc(kw[c]);
+                    const int at = kept + before;
+                    if (((mine >> (tid & 31)) & 1u) && at < max_det) {
+                        soa_store(kept_box, at, soa_load(chunk_box, tid));
+                        if (ARRAY) {
+                            aa.keep[at] = static_cast<int32_t>(key_cand(S.keys[c0 + tid]));
+                        } else {
+                            S.kept_key[at] = S.keys[c0 + tid];
+                            S.kept_raw[at] = S.raw[c0 + tid];
+                        }
+                    }
                 }
             }
-            kept += __popcll(keep);
+            kept += added;
             __syncthreads();
             K2_ACC(12);
-        }
-        if (window) {  // the count filter below needs every survivor's box (single tranche holds them all)
-            for (int i = decoded_upto + tid; i < n_use; i += kThreads) {
-                int cand = static_cast<int>(key_cand(S.keys[i]));
-                const Plan &Q = pass_of(P, X, cand);
-                S.raw[i] = candidate_xyxy(Q, img, cand);
-            }
-            __syncthreads();
         }
         K2_STAMP(4);
         K2_ACC_FLUSH();
@@ -519,150 +645,197 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
     }
     // ---- 5. postprocess_bbox: a kept box survives iff more than one candidate overlaps it by > thr ----------
     if (window) {
-        // 1 < M < 3000 <= tranche capacity: the single tranche holds every survivor, boxes decoded for all
+        // Every survivor counts, not only the ones the walk visited: they are streamed in blocks of kTranche -- the
+        // (single, sorted) tranche still in shared memory when it holds them all, the image's key list otherwise.
         const int warp = tid >> 5, lane = tid & 31;
-        const int mm = min(n_tranche, limit);
-        if (!P.merge_boxes) {
-            // offset boxes + areas once per survivor (in place: the raw boxes of the kept rows live in kept_raw).
-            // The 4096-px class offset keeps boxes of different classes disjoint in x as long as the raw boxes span at
-            // most 4095 px: for classes a < b, fl(x2 + 4096 a) - fl(x1' + 4096 b) <= (max x2 - min x1) - 4096 + 0.5 < 0
-            // (offset values stay below 2^23, so each rounding moves them by at most 0.25).  Then a kept box only needs
-            // the survivors of its own class: bucket the survivors by class (counting sort of their indices in shared
-            // memory) and walk one bucket per kept box instead of all M survivors.  Otherwise (huge boxes -- the
-            // reference then lets classes interact) every pair is tested.
-            int lo_x = 0x7fffffff, hi_x = static_cast<int>(0x80000000u);
-            bool finite = true;
-            for (int j = tid; j < mm; j += kThreads) {
-                const uint64_t key = S.keys[j];
-                const float off = P.class_aware ? __fmul_rn(static_cast<float>(key_cls(key)), 4096.0f) : 0.0f;
-                const float4 rb = S.raw[j];
-                finite = finite && (fabsf(rb.x) <= 3.0e38f) && (fabsf(rb.z) <= 3.0e38f);  // false for NaN / inf
-                lo_x = min(lo_x, float_ordered(rb.x));
-                hi_x = max(hi_x, float_ordered(rb.z));
-                const OffBox b = make_offbox(rb, off);
-                S.raw[j] = make_float4(b.x1, b.y1, b.x2, b.y2);
-                S.area[j] = b.area;
-            }
-            lo_x = __reduce_min_sync(0xffffffffu, lo_x);
-            hi_x = __reduce_max_sync(0xffffffffu, hi_x);
-            if (tid == 0) { S.sel_digit = 0x7fffffff; S.sel_above = static_cast<int>(0x80000000u); }
-            const bool all_finite = __syncthreads_and(finite ? 1 : 0);
-            if (lane == 0) { atomicMin(&S.sel_digit, lo_x); atomicMax(&S.sel_above, hi_x); }
-            __syncthreads();
-            const float span = __fsub_rn(ordered_float(S.sel_above), ordered_float(S.sel_digit));
-            const bool buckets = P.class_aware && thr.positive && P.C <= kThreads && all_finite && span <= 4095.0f;
-            if (buckets) {
-                uint32_t *cnt_cls = S.hist;                 // [0, C]: bucket starts; [kThreads, kThreads + C): fill cursors
-                uint16_t *order = reinterpret_cast<uint16_t *>(S.raw + 3072);  // mm < 3000: the tail of raw[] is free
-                cnt_cls[tid] = 0;
-                __syncthreads();
-                for (int j = tid; j < mm; j += kThreads) atomicAdd(&cnt_cls[key_cls(S.keys[j])], 1u);
-                __syncthreads();
-                // exclusive scan over the classes (one per thread)
-                const uint32_t mine = cnt_cls[tid];
-                uint32_t incl = mine;
+        const bool resident = M <= kTranche;            // then n_tranche == M and S.keys / S.raw[0..decoded_upto) are valid
+        const int total = resident ? min(n_tranche, limit) : M;   // FCOS (top-k) only ever gets here with M <= 300
+        for (int r = tid; r < kept; r += THREADS) {
+            S.kept_cnt[r] = 0;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += v;
-                }
-                if (lane == 31) S.warp_tmp[warp] = incl;
+            for (int q = 0; q < 5; ++q) S.kept_acc[r][q] = 0.0f;
+        }
+        // x-span of the kept boxes: part of the cross-class disjointness test of every block
+        int k_lo = 0x7fffffff, k_hi = static_cast<int>(0x80000000u);
+        bool k_fin = true;
+        for (int r = tid; r < kept; r += THREADS) {
+            const float4 rb = S.kept_raw[r];
+            k_fin = k_fin && (fabsf(rb.x) <= 3.0e38f) && (fabsf(rb.z) <= 3.0e38f);
+            k_lo = min(k_lo, float_ordered(rb.x));
+            k_hi = max(k_hi, float_ordered(rb.z));
+        }
+        for (int b0 = 0; b0 < total; b0 += kTranche) {
+            const int mm = min(kTranche, total - b0);
+            __syncthreads();
+            if (!resident) {
+                for (int i = tid; i < mm; i += THREADS) S.keys[i] = __ldg(keys + b0 + i);
                 __syncthreads();
-                if (warp == 0) {
-                    uint32_t w = S.warp_tmp[lane];
+                decode_boxes<false, EXTRA, THREADS, KEEP>(S, P, X, aa, img, 0, mm);
+            } else if (decoded_upto < mm) {
+                decode_boxes<false, EXTRA, THREADS, KEEP>(S, P, X, aa, img, decoded_upto, mm);
+            }
+            __syncthreads();
+            if (!P.merge_boxes) {
+                // offset boxes + areas once per survivor (in place).  The 4096-px class offset keeps boxes of different
+                // classes disjoint in x as long as the raw boxes span at most 4095 px: for classes a < b,
+                // fl(x2 + 4096 a) - fl(x1' + 4096 b) <= (max x2 - min x1) - 4096 + 0.5 < 0 (offset values stay below 2^23,
+                // so each rounding moves them by at most 0.25).  Then a kept box only needs the survivors of its own
+                // class: bucket the block by class (counting sort of indices in shared memory) and walk one bucket per
+                // kept box.  Otherwise (huge boxes -- the reference then lets classes interact) every pair is tested.
+                int lo_x = k_lo, hi_x = k_hi;
+                bool finite = k_fin;
+                for (int jj = tid; jj < mm; jj += THREADS) {
+                    const uint64_t key = S.keys[jj];
+                    const float off = P.class_aware ? __fmul_rn(static_cast<float>(key_cls(key)), 4096.0f) : 0.0f;
+                    const float4 rb = S.raw[jj];
+                    finite = finite && (fabsf(rb.x) <= 3.0e38f) && (fabsf(rb.z) <= 3.0e38f);  // false for NaN / inf
+                    lo_x = min(lo_x, float_ordered(rb.x));
+                    hi_x = max(hi_x, float_ordered(rb.z));
+                    const OffBox b = make_offbox(rb, off);
+                    S.raw[jj] = make_float4(b.x1, b.y1, b.x2, b.y2);
+                    S.area[jj] = b.area;
+                }
+                lo_x = __reduce_min_sync(0xffffffffu, lo_x);
+                hi_x = __reduce_max_sync(0xffffffffu, hi_x);
+                if (tid == 0) { S.span_lo = 0x7fffffff; S.span_hi = static_cast<int>(0x80000000u); }
+                const bool all_finite = __syncthreads_and(finite ? 1 : 0);
+                if (lane == 0) { atomicMin(&S.span_lo, lo_x); atomicMax(&S.span_hi, hi_x); }
+                __syncthreads();
+                const float span = __fsub_rn(ordered_float(S.span_hi), ordered_float(S.span_lo));
+                const bool buckets = P.class_aware && thr.positive && P.C <= kBins / 2 && all_finite && span <= 4095.0f;
+                if (buckets) {
+                    uint32_t *cnt_cls = S.hist;               // [0, C): bucket starts; [kBins/2, kBins/2 + C): fill cursors
+                    uint32_t *cursor = S.hist + kBins / 2;
+                    for (int c = tid; c < kBins / 2; c += THREADS) cnt_cls[c] = 0;
+                    __syncthreads();
+                    for (int jj = tid; jj < mm; jj += THREADS) atomicAdd(&cnt_cls[key_cls(S.keys[jj])], 1u);
+                    __syncthreads();
+                    // exclusive scan over the classes: PERC consecutive classes per thread
+                    constexpr int PERC = (kBins / 2) / THREADS;
+                    uint32_t mine[PERC];
+                    uint32_t part = 0;
+#pragma unroll
+                    for (int q = 0; q < PERC; ++q) { mine[q] = cnt_cls[PERC * tid + q]; part += mine[q]; }
+                    uint32_t incl = part;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t v = __shfl_up_sync(0xffffffffu, w, d);
-                        if (lane >= d) w += v;
+                        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += v;
                     }
-                    S.warp_tmp[lane] = w;  // inclusive over warps
-                }
-                __syncthreads();
-                const uint32_t start = incl - mine + (warp > 0 ? S.warp_tmp[warp - 1] : 0u);
-                cnt_cls[tid] = start;
-                S.hist[kThreads + tid] = start;
-                __syncthreads();
-                for (int j = tid; j < mm; j += kThreads) {
-                    const uint32_t at = atomicAdd(&S.hist[kThreads + key_cls(S.keys[j])], 1u);
-                    order[at] = static_cast<uint16_t>(j);
-                }
-                __syncthreads();
-                for (int r = warp; r < kept; r += kThreads / 32) {
-                    const OffBox br = soa_load(kept_box, r);
-                    const uint32_t cls_r = key_cls(S.kept_key[r]);
-                    const int lo = static_cast<int>(cnt_cls[cls_r]), hi = static_cast<int>(S.hist[kThreads + cls_r]);
-                    int c = 0;
-                    for (int q = lo + lane; q < hi; q += 32) {
-                        const int j = order[q];
-                        const float4 o = S.raw[j];
-                        const float dw = __fsub_rn(fminf(br.x2, o.z), fmaxf(br.x1, o.x));
-                        const float dh = __fsub_rn(fminf(br.y2, o.w), fmaxf(br.y1, o.y));
-                        if (!(dw > 0.0f && dh > 0.0f)) continue;
-                        c += iou_decide<true>(dw, dh, br.area, S.area[j], thr) ? 1 : 0;
+                    if (lane == 31) S.warp_tmp[warp] = incl;
+                    __syncthreads();
+                    if (warp == 0) {
+                        uint32_t w = lane < THREADS / 32 ? S.warp_tmp[lane] : 0u;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const uint32_t v = __shfl_up_sync(0xffffffffu, w, d);
+                            if (lane >= d) w += v;
+                        }
+                        S.warp_tmp[lane] = w;  // inclusive over warps
                     }
-                    c = __reduce_add_sync(0xffffffffu, c);
-                    if (lane == 0) S.kept_flag[r] = c > 1;
+                    __syncthreads();
+                    uint32_t start = incl - part + (warp > 0 ? S.warp_tmp[warp - 1] : 0u);
+#pragma unroll
+                    for (int q = 0; q < PERC; ++q) {
+                        cnt_cls[PERC * tid + q] = start;
+                        cursor[PERC * tid + q] = start;
+                        start += mine[q];
+                    }
+                    __syncthreads();
+                    for (int jj = tid; jj < mm; jj += THREADS) {
+                        const uint32_t at = atomicAdd(&cursor[key_cls(S.keys[jj])], 1u);
+                        S.order[at] = static_cast<uint16_t>(jj);
+                    }
+                    __syncthreads();
+                    for (int r = warp; r < kept; r += THREADS / 32) {
+                        const OffBox br = soa_load(kept_box, r);
+                        const uint32_t cls_r = key_cls(S.kept_key[r]);
+                        const int lo = static_cast<int>(cnt_cls[cls_r]), hi = static_cast<int>(cursor[cls_r]);
+                        int c = 0;
+                        for (int q = lo + lane; q < hi; q += 32) {
+                            const int jj = S.order[q];
+                            const float4 o = S.raw[jj];
+                            const float dw = __fsub_rn(fminf(br.x2, o.z), fmaxf(br.x1, o.x));
+                            const float dh = __fsub_rn(fminf(br.y2, o.w), fmaxf(br.y1, o.y));
+                            if (!(dw > 0.0f && dh > 0.0f)) continue;
+                            c += iou_decide<true>(dw, dh, br.area, S.area[jj], thr) ? 1 : 0;
+                        }
+                        c = __reduce_add_sync(0xffffffffu, c);
+                        if (lane == 0) S.kept_cnt[r] = static_cast<uint16_t>(S.kept_cnt[r] + c);
+                    }
+                } else {
+                    for (int r = warp; r < kept; r += THREADS / 32) {
+                        const OffBox br = soa_load(kept_box, r);
+                        int c = 0;
+                        for (int jj = lane; jj < mm; jj += 32) {
+                            const float4 o = S.raw[jj];  // offset box (x1, y1, x2, y2)
+                            const float dw = __fsub_rn(fminf(br.x2, o.z), fmaxf(br.x1, o.x));
+                            const float dh = __fsub_rn(fminf(br.y2, o.w), fmaxf(br.y1, o.y));
+                            if (thr.positive && !(dw > 0.0f && dh > 0.0f)) continue;
+                            c += iou_decide<true>(dw, dh, br.area, S.area[jj], thr) ? 1 : 0;
+                        }
+                        c = __reduce_add_sync(0xffffffffu, c);
+                        if (lane == 0) S.kept_cnt[r] = static_cast<uint16_t>(S.kept_cnt[r] + c);
+                    }
                 }
             } else {
-            for (int r = warp; r < kept; r += kThreads / 32) {
-                const OffBox br = soa_load(kept_box, r);
-                int c = 0;
-                for (int j = lane; j < mm; j += 32) {
-                    const float4 o = S.raw[j];  // offset box (x1, y1, x2, y2)
-                    const float dw = __fsub_rn(fminf(br.x2, o.z), fmaxf(br.x1, o.x));
-                    const float dh = __fsub_rn(fminf(br.y2, o.w), fmaxf(br.y1, o.y));
-                    if (thr.positive && !(dw > 0.0f && dh > 0.0f)) continue;
-                    c += iou_decide<true>(dw, dh, br.area, S.area[j], thr) ? 1 : 0;
-                }
-                c = __reduce_add_sync(0xffffffffu, c);
-                if (lane == 0) S.kept_flag[r] = c > 1;
-            }
-            }
-        } else {
-        for (int r = warp; r < kept; r += kThreads / 32) {
-            const OffBox br = soa_load(kept_box, r);
-            int c = 0;
-            float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f, ws = 0.f;
-            for (int j = lane; j < mm; j += 32) {
-                const uint64_t key = S.keys[j];
-                const float off = P.class_aware ? __fmul_rn(static_cast<float>(key_cls(key)), 4096.0f) : 0.0f;
-                const float4 rj = S.raw[j];
-                if (iou_reaches<true>(br, make_offbox(rj, off), thr)) {
-                    ++c;
-                    // trainer/eval_retinanet.py:346-349 (float32 weights, float32 dot)
-                    const float w = key_score(key);
-                    ax = __fadd_rn(ax, __fmul_rn(w, rj.x));
-                    ay = __fadd_rn(ay, __fmul_rn(w, rj.y));
-                    az = __fadd_rn(az, __fmul_rn(w, rj.z));
-                    aw = __fadd_rn(aw, __fmul_rn(w, rj.w));
-                    ws = __fadd_rn(ws, w);
-                }
-            }
-            c = __reduce_add_sync(0xffffffffu, c);
+                for (int r = warp; r < kept; r += THREADS / 32) {
+                    const OffBox br = soa_load(kept_box, r);
+                    int c = 0;
+                    float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f, ws = 0.f;
+                    for (int jj = lane; jj < mm; jj += 32) {
+                        const uint64_t key = S.keys[jj];
+                        const float off = P.class_aware ? __fmul_rn(static_cast<float>(key_cls(key)), 4096.0f) : 0.0f;
+                        const float4 rj = S.raw[jj];
+                        if (iou_reaches<true>(br, make_offbox(rj, off), thr)) {
+                            ++c;
+                            // trainer/eval_retinanet.py:346-349 (float32 weights, float32 dot)
+                            const float w = key_score(key);
+                            ax = __fadd_rn(ax, __fmul_rn(w, rj.x));
+                            ay = __fadd_rn(ay, __fmul_rn(w, rj.y));
+                            az = __fadd_rn(az, __fmul_rn(w, rj.z));
+                            aw = __fadd_rn(aw, __fmul_rn(w, rj.w));
+                            ws = __fadd_rn(ws, w);
+                        }
+                    }
+                    c = __reduce_add_sync(0xffffffffu, c);
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                ax = __fadd_rn(ax, __shfl_xor_sync(0xffffffffu, ax, d));
-                ay = __fadd_rn(ay, __shfl_xor_sync(0xffffffffu, ay, d));
-                az = __fadd_rn(az, __shfl_xor_sync(0xffffffffu, az, d));
-                aw = __fadd_rn(aw, __shfl_xor_sync(0xffffffffu, aw, d));
-                ws = __fadd_rn(ws, __shfl_xor_sync(0xffffffffu, ws, d));
-            }
-            if (lane == 0) {
-                S.kept_flag[r] = c > 1;
-                const float den = __fadd_rn(ws, 1e-16f);
-                S.kept_raw[r] = make_float4(__fdiv_rn(ax, den), __fdiv_rn(ay, den), __fdiv_rn(az, den), __fdiv_rn(aw, den));
+                    for (int d = 16; d > 0; d >>= 1) {
+                        ax = __fadd_rn(ax, __shfl_xor_sync(0xffffffffu, ax, d));
+                        ay = __fadd_rn(ay, __shfl_xor_sync(0xffffffffu, ay, d));
+                        az = __fadd_rn(az, __shfl_xor_sync(0xffffffffu, az, d));
+                        aw = __fadd_rn(aw, __shfl_xor_sync(0xffffffffu, aw, d));
+                        ws = __fadd_rn(ws, __shfl_xor_sync(0xffffffffu, ws, d));
+                    }
+                    if (lane == 0) {
+                        S.kept_cnt[r] = static_cast<uint16_t>(S.kept_cnt[r] + c);
+                        S.kept_acc[r][0] = __fadd_rn(S.kept_acc[r][0], ax);
+                        S.kept_acc[r][1] = __fadd_rn(S.kept_acc[r][1], ay);
+                        S.kept_acc[r][2] = __fadd_rn(S.kept_acc[r][2], az);
+                        S.kept_acc[r][3] = __fadd_rn(S.kept_acc[r][3], aw);
+                        S.kept_acc[r][4] = __fadd_rn(S.kept_acc[r][4], ws);
+                    }
+                }
             }
         }
+        __syncthreads();
+        for (int r = tid; r < kept; r += THREADS) {
+            S.kept_flag[r] = S.kept_cnt[r] > 1;
+            if (P.merge_boxes) {
+                const float den = __fadd_rn(S.kept_acc[r][4], 1e-16f);
+                S.kept_raw[r] = make_float4(__fdiv_rn(S.kept_acc[r][0], den), __fdiv_rn(S.kept_acc[r][1], den),
+                                            __fdiv_rn(S.kept_acc[r][2], den), __fdiv_rn(S.kept_acc[r][3], den));
+            }
         }
     } else {
-        for (int r = tid; r < kept; r += kThreads) S.kept_flag[r] = 1;
+        for (int r = tid; r < kept; r += THREADS) S.kept_flag[r] = 1;
     }
-    if (tid == 0) S.out_count = 0;
     __syncthreads();
     K2_STAMP(5);
     // ---- ordered write of the surviving rows ---------------------------------------------------------------
-    {
-        const int r = tid;  // kept <= kMaxKeep == kThreads
+    int written = 0;
+    for (int r0 = 0; r0 < kept; r0 += THREADS) {
+        const int r = r0 + tid;
         bool pass = false;
         float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
         uint64_t key = 0;
@@ -674,10 +847,15 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
                 pass = (__fsub_rn(box.z, box.x) > P.min_box_wh) && (__fsub_rn(box.w, box.y) > P.min_box_wh);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, pass);
+        __syncthreads();   // warp_tmp of the previous round has been read
         if ((tid & 31) == 0) S.warp_tmp[tid >> 5] = __popc(bal);
         __syncthreads();
-        int before = 0;
-        for (int w = 0; w < (tid >> 5); ++w) before += S.warp_tmp[w];
+        int before = written, total = written;
+        for (int w = 0; w < THREADS / 32; ++w) {
+            const int c = static_cast<int>(S.warp_tmp[w]);
+            if (w < (tid >> 5)) before += c;
+            total += c;
+        }
         if (pass) {
             const int at = before + __popc(bal & ((1u << (tid & 31)) - 1u));
             const float sc = key_score(key);
@@ -695,42 +873,74 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
             }
             if (det_idx) det_idx[static_cast<size_t>(img) * max_det + at] = static_cast<int32_t>(key_cand(key));
         }
-        K2_STAMP(6);
-        if (tid == kThreads - 1) {
-            const int total = before + __popc(bal);
-            const int value = (total == 0 && P.none_when_empty) ? -1 : total;
-            if (G.world > 0) {
-                for (int d = 0; d < G.world; ++d) G.cnt[d][img] = value;
-            } else {
-                det_cnt[img] = value;
-            }
-        }
+        written = total;
+    }
+    K2_STAMP(6);
+    if (tid == 0) {
+        const int value = (written == 0 && P.none_when_empty) ? -1 : written;
         if (G.world > 0) {
-            // release: every row / count store of this CTA is ordered before the arrival count each peer will see
-            __threadfence_system();
-            __syncthreads();
-            if (tid < G.world) atomicAdd_system(G.arrived[tid], 1u);
+            for (int d = 0; d < G.world; ++d) G.cnt[d][img] = value;
+        } else {
+            det_cnt[img] = value;
         }
     }
+    if (G.world > 0) {
+        // release: every row / count store of this CTA is ordered before the arrival count each peer will see
+        __threadfence_system();
+        __syncthreads();
+        if (tid < G.world) atomicAdd_system(G.arrived[tid], 1u);
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+// CTA flavour: 512 threads x 2 per SM when there are more images than SMs (and the kept list is short enough for two
+// CTAs' shared memory), else 1024 threads.  Profiling builds can force it (ysb_debug_set_nms_threads).
+static int g_force_threads = 0;
+void debug_set_nms_threads(int t) { g_force_threads = t; }
+
+static int device_sm_count()
+{
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+}
+
+template <typename EXTRA, int THREADS, int KEEP>
+static cudaError_t launch_flavour(const Plan &P, const EXTRA &X, const uint64_t *d_keys, int64_t key_cap, const int32_t *d_counts,
+                                  float *d_dets, int32_t *d_det_idx, int32_t *d_det_cnt, cudaStream_t stream, const GatherSink &G)
+{
+    // per-device attribute; set on every launch (host-side, sub-microsecond) so that a process driving several
+    // devices never launches with the default 48 KB limit
+    auto kern = k_select_nms<false, EXTRA, THREADS, KEEP>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(NmsSmem<KEEP>)));
+    if (e != cudaSuccess) return e;
+    ArrayArgs aa{};
+    kern<<<P.batch, THREADS, sizeof(NmsSmem<KEEP>), stream>>>(P, X, d_keys, key_cap, d_counts, d_dets, d_det_idx, d_det_cnt, aa, G);
+    return cudaGetLastError();
+}
+
+template <typename EXTRA>
+static cudaError_t launch_any(const Plan &P, const EXTRA &X, const uint64_t *d_keys, int64_t key_cap, const int32_t *d_counts,
+                              float *d_dets, int32_t *d_det_idx, int32_t *d_det_cnt, cudaStream_t stream, const GatherSink *sink)
+{
+    if (P.batch == 0) return cudaSuccess;
+    GatherSink G;
+    if (sink) G = *sink;
+    else memset(&G, 0, sizeof(G));
+    const bool small_keep = P.max_det <= 320;
+    int threads = (small_keep && P.batch > device_sm_count()) ? 512 : 1024;
+    if (g_force_threads == 512 && small_keep) threads = 512;
+    if (g_force_threads == 1024) threads = 1024;
+    if (!small_keep) return launch_flavour<EXTRA, 1024, 1024>(P, X, d_keys, key_cap, d_counts, d_dets, d_det_idx, d_det_cnt, stream, G);
+    if (threads == 512) return launch_flavour<EXTRA, 512, 320>(P, X, d_keys, key_cap, d_counts, d_dets, d_det_idx, d_det_cnt, stream, G);
+    return launch_flavour<EXTRA, 1024, 320>(P, X, d_keys, key_cap, d_counts, d_dets, d_det_idx, d_det_cnt, stream, G);
 }
 
 cudaError_t launch_select_nms(const Plan &P, const uint64_t *d_keys, int64_t key_cap, const int32_t *d_counts,
                               float *d_dets, int32_t *d_det_idx, int32_t *d_det_cnt, cudaStream_t stream,
                               const GatherSink *sink)
 {
-    if (P.batch == 0) return cudaSuccess;
-    // per-device attribute; set on every launch (host-side, sub-microsecond) so that a process driving several
-    // devices never launches with the default 48 KB limit
-    cudaError_t e = cudaFuncSetAttribute(k_select_nms<false, NoExtraPasses>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(sizeof(NmsSmem)));
-    if (e != cudaSuccess) return e;
-    ArrayArgs aa{};
-    GatherSink G;
-    if (sink) G = *sink;
-    else memset(&G, 0, sizeof(G));
-    k_select_nms<false, NoExtraPasses><<<P.batch, kThreads, sizeof(NmsSmem), stream>>>(
-        P, NoExtraPasses{}, d_keys, key_cap, d_counts, d_dets, d_det_idx, d_det_cnt, aa, G);
-    return cudaGetLastError();
+    return launch_any(P, NoExtraPasses{}, d_keys, key_cap, d_counts, d_dets, d_det_idx, d_det_cnt, stream, sink);
 }
 
 // test-time augmentation: one selection/NMS over the key lists the passes appended to; X describes passes 1..n
@@ -738,16 +948,7 @@ cudaError_t launch_select_nms_tta(const Plan &P, const ExtraPasses &X, const uin
                                   const int32_t *d_counts, float *d_dets, int32_t *d_det_idx, int32_t *d_det_cnt,
                                   cudaStream_t stream)
 {
-    if (P.batch == 0) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(k_select_nms<false, ExtraPasses>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(sizeof(NmsSmem)));
-    if (e != cudaSuccess) return e;
-    ArrayArgs aa{};
-    GatherSink G;
-    memset(&G, 0, sizeof(G));
-    k_select_nms<false, ExtraPasses><<<P.batch, kThreads, sizeof(NmsSmem), stream>>>(P, X, d_keys, key_cap, d_counts, d_dets,
-                                                                                      d_det_idx, d_det_cnt, aa, G);
-    return cudaGetLastError();
+    return launch_any(P, X, d_keys, key_cap, d_counts, d_dets, d_det_idx, d_det_cnt, stream, nullptr);
 }
 
 // ---- array flavour: utils.numba_nms / utils.gpu_nms over one explicit (m,4)/(m) pair ---------------------------
@@ -794,8 +995,9 @@ cudaError_t launch_array_nms(const float *d_boxes, const float *d_scores, int64_
     cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int32_t) * 4, stream);
     if (e != cudaSuccess) return e;
     k_array_keys<<<static_cast<unsigned>((m + 255) / 256), 256, 0, stream>>>(d_scores, static_cast<int>(m), keys, counts);
-    e = cudaFuncSetAttribute(k_select_nms<true, NoExtraPasses>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(sizeof(NmsSmem)));
+    // the kept list of the array flavour lives in the global workspace: the shared-memory kept arrays stay minimal
+    auto kern = k_select_nms<true, NoExtraPasses, 1024, 64>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(NmsSmem<64>)));
     if (e != cudaSuccess) return e;
     Plan P;
     memset(&P, 0, sizeof(P));
@@ -813,8 +1015,7 @@ cudaError_t launch_array_nms(const float *d_boxes, const float *d_scores, int64_
     aa.thr32 = static_cast<float>(iou_thr);
     GatherSink G;
     memset(&G, 0, sizeof(G));
-    k_select_nms<true, NoExtraPasses><<<1, kThreads, sizeof(NmsSmem), stream>>>(P, NoExtraPasses{}, keys, m, counts, nullptr,
-                                                                                 nullptr, nullptr, aa, G);
+    kern<<<1, 1024, sizeof(NmsSmem<64>), stream>>>(P, NoExtraPasses{}, keys, m, counts, nullptr, nullptr, nullptr, aa, G);
     return cudaGetLastError();
 }
 
