@@ -17,6 +17,7 @@
  *   ysb_postprocess_tta   the same with hyp['use_tta']     trainer/eval_yolov5.py:30-42 + 152-179 (test_time_augmentation)
  *   ysb_decode_into       one pass of test_time_augmentation (decode + scale/flip undo + concat slot)
  *   ysb_elementwise_iou_backward  autograd of the three      loss/yolov5_loss.py:110, yolov7_loss.py:130, yolov8_loss.py:306
+ *   ysb_pairwise_iou_backward     autograd of utils.gpu_iou  loss/yolox_loss.py:133, loss/yolov7_loss.py:312
  *   ysb_soft_nms          utils.gpu_*_soft_nms             utils/nms.py:68-140
  *   ysb_undo_letterbox    box half of preds_postprocess    val_yolov5.py:166-172
  *   ysb_nms               utils.numba_nms / utils.gpu_nms  utils/nms.py:10-27 / 30-65
@@ -195,6 +196,14 @@ int ysb_nms(const float *d_boxes, const float *d_scores, int64_t m, double iou_t
  * constant).  float32 throughout. */
 int ysb_elementwise_iou_backward(const float *d_b1, int64_t n1, const float *d_b2, int64_t n2, int iou_kind,
                                  const float *d_grad_out, float *d_grad_b1, float *d_grad_b2, void *stream);
+
+/* Backward of the float32 pairwise IoU (ysb_pairwise_iou with YSB_IOU_F32 = utils.gpu_iou, utils/bbox_tools.py:164-190):
+ * the label assignment of loss/yolox_loss.py:133 and loss/yolov7_loss.py:312 calls gpu_iou(tar_box, pred_box) with grad
+ * enabled (`torch.no_grad()` at yolox_loss.py:92 is a bare statement, not a decorator), so patching utils.gpu_iou needs it.
+ * d_grad_out (n, m) -> dL/d_b1 (n,4) = sum over columns, dL/d_b2 (m,4) = sum over rows (float64 accumulation, float32
+ * results).  Either gradient pointer may be NULL.  All box / gradient pointers 16-byte aligned. */
+int ysb_pairwise_iou_backward(const float *d_b1, int64_t n, const float *d_b2, int64_t m, const float *d_grad_out,
+                              float *d_grad_b1, float *d_grad_b2, void *stream);
 
 /* Soft-NMS (utils/nms.py:68-140; no caller in the reference, float32 GIoU/DIoU/CIoU flavours only -- 'iou' is broken
  * there).  Repeats: pick the first arg-max, record processed[idx] = its current score, decay every score whose IoU with

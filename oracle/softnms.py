@@ -195,3 +195,35 @@ def iou_backward(kind, b1, b2, grad_out):
     if bc:
         ga = ga.sum(axis=0, keepdims=True)
     return ga, gb
+
+
+def pairwise_iou_backward(b1, b2, grad_out):
+    """Backward of utils.gpu_iou (utils/bbox_tools.py:164-190): d sum(grad_out * iou(b1, b2)) / d b1 (N,4), d b2 (M,4),
+    float64 on float32 inputs.  prod -> w*h; torch.min/max split ties evenly; clamp(min=0.0) and clamp(1e-9) pass the
+    gradient on their bound.  Pinned by tests/golden/utils_extra.npz (torch autograd through the reference's function)."""
+    a = np.asarray(b1, dtype=np.float64).reshape(-1, 1, 4)
+    b = np.asarray(b2, dtype=np.float64).reshape(1, -1, 4)
+    G = np.asarray(grad_out, dtype=np.float64).reshape(a.shape[0], b.shape[1])
+    w1, h1 = a[..., 2] - a[..., 0], a[..., 3] - a[..., 1]
+    w2, h2 = b[..., 2] - b[..., 0], b[..., 3] - b[..., 1]
+    tw = np.minimum(a[..., 2], b[..., 2]) - np.maximum(a[..., 0], b[..., 0])
+    th = np.minimum(a[..., 3], b[..., 3]) - np.maximum(a[..., 1], b[..., 1])
+    iw, ih = np.maximum(tw, 0.0), np.maximum(th, 0.0)
+    inter = iw * ih
+    u_raw = w1 * h1 + w2 * h2 - inter
+    uc = np.maximum(u_raw, 1e-9)
+    d_uraw = np.where(u_raw >= 1e-9, -G * inter / uc ** 2, 0.0)
+    d_inter = G / uc - d_uraw
+    d_tw = np.where(tw >= 0, d_inter * ih, 0.0)
+    d_th = np.where(th >= 0, d_inter * iw, 0.0)
+    n, m = G.shape
+    ga = np.zeros((n, m, 4))
+    gb = np.zeros((n, m, 4))
+    ga[..., 0], ga[..., 1], ga[..., 2], ga[..., 3] = -d_uraw * h1, -d_uraw * w1, d_uraw * h1, d_uraw * w1
+    gb[..., 0], gb[..., 1], gb[..., 2], gb[..., 3] = -d_uraw * h2, -d_uraw * w2, d_uraw * h2, d_uraw * w2
+    for lo, hi, d_t in ((0, 2, d_tw), (1, 3, d_th)):
+        p, q = _split_max(np.broadcast_to(a[..., lo], (n, m)), np.broadcast_to(b[..., lo], (n, m)), -d_t)
+        ga[..., lo] += p; gb[..., lo] += q
+        p, q = _split_min(np.broadcast_to(a[..., hi], (n, m)), np.broadcast_to(b[..., hi], (n, m)), d_t)
+        ga[..., hi] += p; gb[..., hi] += q
+    return ga.sum(axis=1), gb.sum(axis=0)

@@ -45,7 +45,7 @@ def golden_names(prefix=""):
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
     # tta_* fixtures hold three head sets and the merged tensor, c1_* fixtures are seed-only full-size cases (heads are
     # regenerated, see full_size_golden): both are asked for explicitly, golden_names("tta_") / golden_names("c1_")
-    return [n for n in names if n.startswith(prefix) and n != "utils_nms_iou"
+    return [n for n in names if n.startswith(prefix) and not n.startswith("utils_")
             and (prefix or not n.startswith(("tta_", "c1_")))]
 
 

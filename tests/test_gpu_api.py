@@ -204,11 +204,51 @@ def test_rowwise_iou_autograd_matches_reference():
         fn(x1, x2).backward(torch.from_numpy(go).cuda())
         r1, r2 = oracle.iou_backward(kind, a, b, go)
         assert close_rel(x1.grad.cpu().numpy(), r1, 1e-5).all() and close_rel(x2.grad.cpu().numpy(), r2, 1e-5).all()
-    # no_grad / detached inputs take the plain forward; the pairwise gpu_iou refuses to be differentiated
+    # no_grad / detached inputs take the plain forward
     with torch.no_grad():
         assert not gpu_CIoU(x1, x2).requires_grad
-    with pytest.raises(NotImplementedError):
-        gpu_iou(x1, x2)
+        assert not gpu_iou(x1, x2).requires_grad
+
+
+def test_pairwise_iou_autograd_matches_reference():
+    """utils.gpu_iou under autograd (ysb_pairwise_iou_backward) vs torch autograd through the reference's own gpu_iou
+    (tests/golden/utils_extra.npz; the call shape of loss/yolox_loss.py:133: targets (N,4) x predictions (M,4) that
+    require grad): |d - ref| <= 1e-5 * max(|ref|, 1)."""
+    from yoloseries_b200.utils import gpu_iou
+    g = load_golden("utils_extra")
+    w = torch.from_numpy(g["pair_w"]).cuda()
+    x1 = torch.from_numpy(g["pair_b1"]).cuda().requires_grad_(True)
+    x2 = torch.from_numpy(g["pair_b2"]).cuda().requires_grad_(True)
+    out = gpu_iou(x1, x2)
+    assert out.requires_grad and out.shape == (37, 150)
+    assert close_rel(out.detach().cpu().numpy(), g["pair_iou"], 1e-5).all()
+    (out * w).sum().backward()
+    for got, key in ((x1.grad, "pair_d1"), (x2.grad, "pair_d2")):
+        err = np.abs(got.cpu().numpy() - g[key]).max()
+        assert close_rel(got.cpu().numpy(), g[key], 1e-5).all(), (key, err)
+        assert err <= 2e-6, (key, err)
+    # the loss case: only the predictions need a gradient, targets are constants; CPU leaves get CPU gradients
+    p = torch.from_numpy(g["pair_b2"]).requires_grad_(True)
+    gpu_iou(torch.from_numpy(g["pair_b1"]), p).sum().backward()
+    assert p.grad.device.type == "cpu"
+    _, r2 = oracle.pairwise_iou_backward(g["pair_b1"], g["pair_b2"], np.ones((37, 150)))
+    assert close_rel(p.grad.numpy(), r2, 1e-5).all()
+    # larger, non-multiple-of-tile shapes against the analytic oracle; empty sides give zero gradients
+    rng = np.random.default_rng(5)
+    for n, m in ((1, 1), (3, 1000), (700, 45), (257, 300)):
+        xy = rng.uniform(0, 300, size=(m, 2)).astype(np.float32)
+        b = np.concatenate((xy, xy + rng.uniform(2, 120, size=(m, 2)).astype(np.float32)), axis=1)
+        xy = rng.uniform(0, 300, size=(n, 2)).astype(np.float32)
+        a = np.concatenate((xy, xy + rng.uniform(2, 120, size=(n, 2)).astype(np.float32)), axis=1)
+        go = rng.uniform(-1, 1, size=(n, m)).astype(np.float32)
+        x1, x2 = torch.from_numpy(a).cuda().requires_grad_(True), torch.from_numpy(b).cuda().requires_grad_(True)
+        gpu_iou(x1, x2).backward(torch.from_numpy(go).cuda())
+        r1, r2 = oracle.pairwise_iou_backward(a, b, go)
+        assert close_rel(x1.grad.cpu().numpy(), r1, 1e-5).all() and close_rel(x2.grad.cpu().numpy(), r2, 1e-5).all(), (n, m)
+    x1 = torch.zeros((0, 4), device="cuda", requires_grad=True)
+    x2 = torch.from_numpy(b).cuda().requires_grad_(True)
+    gpu_iou(x1, x2).sum().backward()
+    assert x1.grad.shape == (0, 4) and torch.count_nonzero(x2.grad).item() == 0
 
 
 def test_soft_nms_matches_reference():

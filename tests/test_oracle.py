@@ -232,3 +232,10 @@ def test_full_size_reference_fixture(name):
     r = oracle.evaluator_nms(meta["family"], own, hyp)[0]
     np.testing.assert_array_equal(r.cand_index, g["cand_index"][0])
     assert close_rel(r.rows, g["rows"][0, :cnt], 1e-5).all()
+
+
+def test_pairwise_iou_backward_matches_reference_autograd():
+    """oracle.pairwise_iou_backward vs torch autograd through the reference's gpu_iou (utils_extra.npz)."""
+    g = load_golden("utils_extra")
+    d1, d2 = oracle.pairwise_iou_backward(g["pair_b1"], g["pair_b2"], g["pair_w"])
+    assert np.abs(d1 - g["pair_d1"]).max() <= 1e-7 and np.abs(d2 - g["pair_d2"]).max() <= 1e-7

@@ -36,6 +36,8 @@ void debug_set_nms_threads(int t);
 
 cudaError_t launch_elementwise_iou_backward(const float *b1, int64_t n1, const float *b2, int64_t n2, int kind,
                                             const float *grad_out, float *g1, float *g2, cudaStream_t stream);
+cudaError_t launch_pairwise_iou_backward(const float *b1, int64_t n, const float *b2, int64_t m, const float *grad_out,
+                                         float *g1, float *g2, cudaStream_t stream);
 cudaError_t launch_soft_nms(const float *boxes, const float *scores, int64_t m, float thr, int kind, int mode, float sigma,
                             void *ws, float *processed, cudaStream_t stream);
 cudaError_t launch_undo_letterbox(float *dets, const int32_t *cnt, int batch, int max_det, const float *info, cudaStream_t stream);
@@ -593,6 +595,19 @@ int ysb_elementwise_iou_backward(const float *d_b1, int64_t n1, const float *d_b
     if (iou_kind != YSB_GIOU && iou_kind != YSB_DIOU && iou_kind != YSB_CIOU) return YSB_ERR_BAD_ARG;
     return cuda_status(launch_elementwise_iou_backward(d_b1, n1, d_b2, n2, iou_kind, d_grad_out, d_grad_b1, d_grad_b2,
                                                        static_cast<cudaStream_t>(stream)));
+}
+
+int ysb_pairwise_iou_backward(const float *d_b1, int64_t n, const float *d_b2, int64_t m, const float *d_grad_out,
+                              float *d_grad_b1, float *d_grad_b2, void *stream)
+{
+    if (n < 0 || m < 0) return YSB_ERR_BAD_ARG;
+    if (n > 0 && m > 0 && (!d_b1 || !d_b2 || !d_grad_out)) return YSB_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_b1) | reinterpret_cast<uintptr_t>(d_b2) | reinterpret_cast<uintptr_t>(d_grad_b1) |
+         reinterpret_cast<uintptr_t>(d_grad_b2)) & 15u)
+        return YSB_ERR_BAD_ARG;  // boxes and gradients move as float4
+    if (n > 0x7fffffffll) return YSB_ERR_LIMIT;
+    return cuda_status(launch_pairwise_iou_backward(d_b1, n, d_b2, m, d_grad_out, d_grad_b1, d_grad_b2,
+                                                    static_cast<cudaStream_t>(stream)));
 }
 
 int ysb_soft_nms(const float *d_boxes, const float *d_scores, int64_t m, float iou_thr, int iou_kind, int mode,

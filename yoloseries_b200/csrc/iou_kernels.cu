@@ -1,5 +1,5 @@
-// iou_kernels.cu -- the IoU routines of utils/bbox_tools.py as standalone kernels (forward only; callers that
-// need autograd keep using the torch expressions, see yoloseries_b200/utils/bbox_tools.py).
+// iou_kernels.cu -- the IoU routines of utils/bbox_tools.py as standalone kernels, forward and (for the flavours the
+// reference's losses differentiate through) backward; see yoloseries_b200/utils/bbox_tools.py.
 //   pairwise  NUMBA_F64MIX  numba_iou  utils/bbox_tools.py:12-35   -> (n, m) float64
 //   pairwise  F32           gpu_iou    utils/bbox_tools.py:164-190 -> (n, m) float32
 //   rowwise   GIoU/DIoU/CIoU           utils/bbox_tools.py:193-339 -> (n) float32, b1 broadcast when it has one row
@@ -182,6 +182,111 @@ __global__ void __launch_bounds__(256) k_elementwise_iou_backward(const float4 *
         atomicAdd(o + 2, ga.x2);
         atomicAdd(o + 3, ga.y2);
     }
+}
+
+// ---- backward of the pairwise gpu_iou (utils/bbox_tools.py:164-190; differentiated by loss/yolox_loss.py:133 and
+// loss/yolov7_loss.py:312, whose label assignment runs with grad enabled: `torch.no_grad()` at yolox_loss.py:92 is a bare
+// statement, not a decorator) --------------------------------------------------------------------------------------
+// Same conventions as above: min/max split ties evenly, clamp(min=0) / clamp(1e-9) pass the gradient on the bound.
+__device__ __forceinline__ void iou_f32_backward(float4 a, float4 b, float G, Grad4 &ga, Grad4 &gb)
+{
+    const float w1 = a.z - a.x, h1 = a.w - a.y, w2 = b.z - b.x, h2 = b.w - b.y;
+    const float tw = fminf(a.z, b.z) - fmaxf(a.x, b.x), th = fminf(a.w, b.w) - fmaxf(a.y, b.y);
+    const float iw = fmaxf(tw, 0.0f), ih = fmaxf(th, 0.0f);
+    const float inter = iw * ih;
+    const float u_raw = w1 * h1 + w2 * h2 - inter;
+    const float uc = fmaxf(u_raw, 1e-9f);
+    float d_inter = G / uc;
+    const float d_uraw = u_raw >= 1e-9f ? -G * inter / (uc * uc) : 0.0f;
+    d_inter -= d_uraw;
+    const float d_w1 = d_uraw * h1, d_h1 = d_uraw * w1, d_w2 = d_uraw * h2, d_h2 = d_uraw * w2;
+    const float d_tw = tw >= 0.0f ? d_inter * ih : 0.0f;
+    const float d_th = th >= 0.0f ? d_inter * iw : 0.0f;
+    ga = Grad4{-d_w1, -d_h1, d_w1, d_h1};
+    gb = Grad4{-d_w2, -d_h2, d_w2, d_h2};
+    max_bwd(a.x, b.x, -d_tw, ga.x1, gb.x1);
+    min_bwd(a.z, b.z, d_tw, ga.x2, gb.x2);
+    max_bwd(a.y, b.y, -d_th, ga.y1, gb.y1);
+    min_bwd(a.w, b.w, d_th, ga.y2, gb.y2);
+}
+
+// g1[i] = sum_j d(G_ij * iou_ij)/d b1_i: one CTA per row i, threads stride over the columns (coalesced reads of G).
+__global__ void __launch_bounds__(256) k_pairwise_iou_bwd_rows(const float4 *__restrict__ b1, const float4 *__restrict__ b2,
+                                                               int64_t m, const float *__restrict__ G, float4 *__restrict__ g1)
+{
+    __shared__ double red[8][4];
+    const int64_t i = blockIdx.x;
+    const float4 a = __ldg(b1 + i);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int64_t j = threadIdx.x; j < m; j += 256) {
+        Grad4 ga, gb;
+        iou_f32_backward(a, __ldg(b2 + j), __ldg(G + i * m + j), ga, gb);
+        s0 += ga.x1; s1 += ga.y1; s2 += ga.x2; s3 += ga.y2;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, d);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+        s3 += __shfl_xor_sync(0xffffffffu, s3, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        double *r = red[threadIdx.x >> 5];
+        r[0] = s0; r[1] = s1; r[2] = s2; r[3] = s3;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int w = 0; w < 8; ++w)
+            for (int c = 0; c < 4; ++c) t[c] += red[w][c];
+        g1[i] = make_float4(static_cast<float>(t[0]), static_cast<float>(t[1]), static_cast<float>(t[2]), static_cast<float>(t[3]));
+    }
+}
+
+// g2[j] = sum_i ...: a CTA owns 32 columns, its 8 thread rows stride over the rows i (each warp reads 32 consecutive
+// G values of one row), partial sums meet in shared memory.
+__global__ void __launch_bounds__(256) k_pairwise_iou_bwd_cols(const float4 *__restrict__ b1, int64_t n,
+                                                               const float4 *__restrict__ b2, int64_t m,
+                                                               const float *__restrict__ G, float4 *__restrict__ g2)
+{
+    __shared__ double red[8][32][4];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * 32 + tx;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (j < m) {
+        const float4 b = __ldg(b2 + j);
+        for (int64_t i = ty; i < n; i += 8) {
+            Grad4 ga, gb;
+            iou_f32_backward(__ldg(b1 + i), b, __ldg(G + i * m + j), ga, gb);
+            s0 += gb.x1; s1 += gb.y1; s2 += gb.x2; s3 += gb.y2;
+        }
+    }
+    double *r = red[ty][tx];
+    r[0] = s0; r[1] = s1; r[2] = s2; r[3] = s3;
+    __syncthreads();
+    if (ty == 0 && j < m) {
+        double t[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int w = 0; w < 8; ++w)
+            for (int c = 0; c < 4; ++c) t[c] += red[w][tx][c];
+        g2[j] = make_float4(static_cast<float>(t[0]), static_cast<float>(t[1]), static_cast<float>(t[2]), static_cast<float>(t[3]));
+    }
+}
+
+cudaError_t launch_pairwise_iou_backward(const float *b1, int64_t n, const float *b2, int64_t m, const float *grad_out,
+                                         float *g1, float *g2, cudaStream_t stream)
+{
+    if (n == 0 || m == 0) {  // an empty sum: zero gradients for whichever side has rows
+        cudaError_t e = cudaSuccess;
+        if (g1 && n > 0) e = cudaMemsetAsync(g1, 0, static_cast<size_t>(n) * 16, stream);
+        if (e == cudaSuccess && g2 && m > 0) e = cudaMemsetAsync(g2, 0, static_cast<size_t>(m) * 16, stream);
+        return e;
+    }
+    const float4 *a = reinterpret_cast<const float4 *>(b1), *b = reinterpret_cast<const float4 *>(b2);
+    if (g1) k_pairwise_iou_bwd_rows<<<static_cast<unsigned>(n), 256, 0, stream>>>(a, b, m, grad_out, reinterpret_cast<float4 *>(g1));
+    if (g2)
+        k_pairwise_iou_bwd_cols<<<static_cast<unsigned>((m + 31) / 32), 256, 0, stream>>>(a, n, b, m, grad_out,
+                                                                                          reinterpret_cast<float4 *>(g2));
+    return cudaGetLastError();
 }
 
 cudaError_t launch_elementwise_iou_backward(const float *b1, int64_t n1, const float *b2, int64_t n2, int kind,

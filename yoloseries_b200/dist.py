@@ -246,21 +246,29 @@ class ShardedPostProcessor:
         self._key_cap = n
         b, d, dev = self.batch, self.max_det, self.device
         self._slots = []
+        cur = torch.cuda.current_stream(dev)
         for s in range(self.lanes):
-            sl = {"keys": torch.empty((b, n), dtype=torch.int64, device=dev),
-                  "counts": torch.zeros((b, 4), dtype=torch.int32, device=dev),
-                  "idx": torch.empty((b, d), dtype=torch.int32, device=dev),
-                  "done": torch.cuda.Event()}
-            if self.mode == "p2p":
-                sl["rows"], sl["cnt"] = self.dg.views(s)
-            elif self.mode == "nccl":
-                sl["send"] = torch.zeros(b * d * 6 + b, dtype=torch.float32, device=dev)
-                sl["recv"] = torch.empty((self.world, b * d * 6 + b), dtype=torch.float32, device=dev)
-                sl["rows"] = sl["recv"][:, : b * d * 6].view(self.world, b, d, 6)
-                sl["cnt"] = sl["recv"][:, b * d * 6:].view(torch.int32)
-            else:
-                sl["rows"] = torch.zeros((1, b, d, 6), dtype=torch.float32, device=dev)
-                sl["cnt"] = torch.zeros((1, b), dtype=torch.int32, device=dev)
+            # A lane's buffers are allocated UNDER the lane's stream: the caching allocator hands out blocks whose last
+            # use may still be pending on the stream they were freed on, which is only safe for work enqueued on that
+            # same stream.  (Allocated on the caller's stream and written from the lane, a key buffer could share memory
+            # with a temporary of a still-running producer kernel: corrupted keys -> wild candidate indices in the NMS
+            # kernel.)  The lane also waits for everything the caller has enqueued so far.
+            self.streams[s].wait_stream(cur)
+            with torch.cuda.stream(self.streams[s]):
+                sl = {"keys": torch.empty((b, n), dtype=torch.int64, device=dev),
+                      "counts": torch.zeros((b, 4), dtype=torch.int32, device=dev),
+                      "idx": torch.empty((b, d), dtype=torch.int32, device=dev),
+                      "done": torch.cuda.Event()}
+                if self.mode == "p2p":
+                    sl["rows"], sl["cnt"] = self.dg.views(s)
+                elif self.mode == "nccl":
+                    sl["send"] = torch.zeros(b * d * 6 + b, dtype=torch.float32, device=dev)
+                    sl["recv"] = torch.empty((self.world, b * d * 6 + b), dtype=torch.float32, device=dev)
+                    sl["rows"] = sl["recv"][:, : b * d * 6].view(self.world, b, d, 6)
+                    sl["cnt"] = sl["recv"][:, b * d * 6:].view(torch.int32)
+                else:
+                    sl["rows"] = torch.zeros((1, b, d, 6), dtype=torch.float32, device=dev)
+                    sl["cnt"] = torch.zeros((1, b), dtype=torch.int32, device=dev)
             self._slots.append(sl)
 
     def _enqueue(self, ptrs, nheads, lane, st, events=None):
@@ -377,7 +385,11 @@ class ShardedPostProcessor:
                 raise RuntimeError(f"detection gather timed out waiting for a peer (code {e})")
 
     def close(self):
+        """Waits for the lanes, then releases the buffers (collective when the p2p gather is in use)."""
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+        self._graphs = {}
         if self.dg is not None:
-            self._graphs = {}
             self.dg.close()
             self.dg = None
+        self._slots, self._ent = None, None

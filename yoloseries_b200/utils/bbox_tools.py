@@ -2,8 +2,10 @@
 
 The row-wise GIoU / DIoU / CIoU are differentiable (torch.autograd.Function over ysb_elementwise_iou /
 ysb_elementwise_iou_backward) because the reference's losses differentiate through them (loss/yolov5_loss.py:110,
-loss/yolov7_loss.py:130, loss/yolov8_loss.py:306, loss/loss.py:109).  Every caller of the pairwise gpu_iou runs under
-no_grad (loss/yolox_loss.py:92-133, loss/yolov7_loss.py:244-312), so that one stays forward-only."""
+loss/yolov7_loss.py:130, loss/yolov8_loss.py:306, loss/loss.py:109).  The pairwise gpu_iou is differentiable too
+(ysb_pairwise_iou_backward): the label assignment of loss/yolox_loss.py:133 and loss/yolov7_loss.py:312 calls it on
+predictions that require grad with grad mode ON (`torch.no_grad()` at yolox_loss.py:92 is a bare statement, not a
+decorator), so the result must carry a grad_fn exactly like the reference's torch expression does."""
 import numpy as np
 import torch
 
@@ -11,13 +13,6 @@ from .. import _lib
 from ._common import stream_ptr, to_cuda_f32
 
 __all__ = ["numba_iou", "gpu_iou", "gpu_Giou", "gpu_DIoU", "gpu_CIoU"]
-
-
-def _no_grad_only(*tensors):
-    if any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
-        raise NotImplementedError(
-            "the pairwise gpu_iou kernel is forward-only: every caller in the reference runs it under no_grad "
-            "(loss/yolox_loss.py:92-133, loss/yolov7_loss.py:244-312); detach the inputs or wrap the call in torch.no_grad()")
 
 
 def numba_iou(bbox1, bbox2):
@@ -31,16 +26,53 @@ def numba_iou(bbox1, bbox2):
     return out.cpu().numpy()
 
 
-def gpu_iou(bbox1, bbox2):
-    """utils/bbox_tools.py:164-190 -- (N,4), (M,4) tensors -> (N,M) float32 tensor on the inputs' device."""
-    if torch.is_grad_enabled():
-        _no_grad_only(bbox1, bbox2)
-    b1, b2 = to_cuda_f32(bbox1.reshape(-1, 4)), to_cuda_f32(bbox2.reshape(-1, 4))
+def _pairwise_forward(b1, b2):
     out = torch.empty((b1.shape[0], b2.shape[0]), dtype=torch.float32, device=b1.device)
     with torch.cuda.device(b1.device):
         _lib.check(_lib.load().ysb_pairwise_iou(b1.data_ptr(), b1.shape[0], b2.data_ptr(), b2.shape[0], _lib.IOU_F32,
                                                 out.data_ptr(), stream_ptr()), "ysb_pairwise_iou")
     return out
+
+
+class _PairwiseIoU(torch.autograd.Function):
+    """forward: ysb_pairwise_iou (float32 flavour); backward: ysb_pairwise_iou_backward (first order only)."""
+
+    @staticmethod
+    def forward(ctx, bbox1, bbox2):
+        b1 = to_cuda_f32(bbox1.reshape(-1, 4))
+        b2 = to_cuda_f32(bbox2.reshape(-1, 4), b1.device)
+        ctx.save_for_backward(b1, b2)
+        ctx.meta = (bbox1.shape, bbox1.dtype, bbox1.device, bbox2.shape, bbox2.dtype, bbox2.device)
+        return _pairwise_forward(b1, b2)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        b1, b2 = ctx.saved_tensors
+        shape1, dtype1, dev1, shape2, dtype2, dev2 = ctx.meta
+        need1, need2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        g = to_cuda_f32(grad_out.reshape(b1.shape[0], b2.shape[0]), b1.device)
+        g1 = torch.empty_like(b1) if need1 else None
+        g2 = torch.empty_like(b2) if need2 else None
+        with torch.cuda.device(b1.device):
+            _lib.check(_lib.load().ysb_pairwise_iou_backward(
+                b1.data_ptr(), b1.shape[0], b2.data_ptr(), b2.shape[0], g.data_ptr(),
+                g1.data_ptr() if need1 else None, g2.data_ptr() if need2 else None, stream_ptr()),
+                "ysb_pairwise_iou_backward")
+        if need1:
+            g1 = g1.reshape(shape1).to(device=dev1, dtype=dtype1)
+        if need2:
+            g2 = g2.reshape(shape2).to(device=dev2, dtype=dtype2)
+        return g1, g2
+
+
+def gpu_iou(bbox1, bbox2):
+    """utils/bbox_tools.py:164-190 -- (N,4), (M,4) tensors -> (N,M) float32 tensor on the inputs' device; differentiable
+    like the reference's torch expression (callers: loss/yolox_loss.py:133, loss/yolov7_loss.py:312)."""
+    if torch.is_grad_enabled() and (bbox1.requires_grad or bbox2.requires_grad):
+        return _PairwiseIoU.apply(bbox1, bbox2)
+    b1 = to_cuda_f32(bbox1.reshape(-1, 4))
+    return _pairwise_forward(b1, to_cuda_f32(bbox2.reshape(-1, 4), b1.device))
 
 
 def _rowwise_forward(kind, b1, b2):
