@@ -20,6 +20,8 @@
  *   ysb_pairwise_iou_backward     autograd of utils.gpu_iou  loss/yolox_loss.py:133, loss/yolov7_loss.py:312
  *   ysb_soft_nms          utils.gpu_*_soft_nms             utils/nms.py:68-140
  *   ysb_undo_letterbox    box half of preds_postprocess    val_yolov5.py:166-172
+ *   ysb_map_iou           utils.mAP.iou                    utils/mAP.py:18-42
+ *   ysb_compute_tp        mAP_v2.compute_tp                utils/mAP.py:70-100
  *   ysb_nms               utils.numba_nms / utils.gpu_nms  utils/nms.py:10-27 / 30-65
  *   ysb_pairwise_iou      utils.numba_iou / utils.gpu_iou  utils/bbox_tools.py:12-35 / 164-190
  *   ysb_elementwise_iou   utils.gpu_Giou/gpu_DIoU/gpu_CIoU utils/bbox_tools.py:193-339
@@ -41,7 +43,7 @@
 extern "C" {
 #endif
 
-#define YSB_ABI_VERSION 3
+#define YSB_ABI_VERSION 4
 #define YSB_MAX_LEVELS 8
 #define YSB_MAX_ANCHORS 9
 #define YSB_MAX_PASSES 4             /* test-time-augmentation passes merged by ysb_postprocess_tta */
@@ -128,6 +130,12 @@ typedef struct ysb_params {
     float tta_scale;
     int32_t tta_flip;          /* 0 none, 2, 3: the reference's flip_axis values */
     int32_t tta_img_h, tta_img_w;
+    /* Optional letterbox undo fused into the row write of ysb_select_nms / ysb_postprocess(_tta) (the first consumer of
+     * the kept rows, val_yolov5.py:166-172 preds_postprocess): DEVICE pointer to (batch, 5) float32
+     * {scale, pad_top, pad_left, org_h, org_w}, or NULL = rows stay in network-input pixels (the reference's evaluator
+     * output).  Same arithmetic as ysb_undo_letterbox; applied after NMS, the postprocess_bbox count filter and
+     * remove_small_boxes, which all see the un-mapped boxes exactly like the reference. */
+    const float *d_letterbox;
 } ysb_params;
 
 int ysb_abi_version(void);
@@ -204,6 +212,25 @@ int ysb_elementwise_iou_backward(const float *d_b1, int64_t n1, const float *d_b
  * results).  Either gradient pointer may be NULL.  All box / gradient pointers 16-byte aligned. */
 int ysb_pairwise_iou_backward(const float *d_b1, int64_t n, const float *d_b2, int64_t m, const float *d_grad_out,
                               float *d_grad_b1, float *d_grad_b2, void *stream);
+
+/* mAP hand-off (the consumer of the kept rows, val_yolov5.py:388 -> utils/mAP.py).
+ * ysb_map_iou: utils/mAP.py:18-42 `iou(box1, box2)` -- rows of row_w1 / row_w2 values whose first four are
+ * (x1, y1, x2, y2); float32 or float64 (is_f64) in, the same type out, (n, m);  inter / clip(a1 + a2 - inter, 1e-6, 1e7).
+ * ysb_compute_tp: utils/mAP.py:70-100 `mAP_v2.compute_tp(gt, pred)` for a batch of images in one launch.  d_gt: all
+ * images' ground-truth rows (x1, y1, x2, y2, cls) concatenated, d_pred: all kept rows (x1, y1, x2, y2, score, cls)
+ * concatenated, *_offsets (batch + 1) int64 row offsets on the device.  iou_thresholds: 10 HOST doubles
+ * (np.linspace(0.5, 0.95, 10)).  d_tp (total_pred, 10) uint8 <- the reference's bool matrix: pairs with
+ * iou >= thr[0] and equal label are ranked by IoU, every prediction keeps its best ground-truth box, every ground-truth
+ * box then keeps the LOWEST-index prediction that chose it (the reference's second np.unique runs over a list ordered
+ * by prediction index), and tp[j, t] = iou >= thr[t] in float64.  Equal IoUs for one prediction: the larger ground-truth
+ * index wins (argsort()[::-1] of a stable sort; numpy's default sort is only stable up to 16 elements -- unpinned beyond).
+ * Workspace: one int32 per ground-truth row. */
+int ysb_map_iou(const void *d_box1, int64_t n, int row_w1, const void *d_box2, int64_t m, int row_w2, int is_f64,
+                void *d_out, void *stream);
+int ysb_compute_tp_workspace_bytes(int64_t total_gt, size_t *bytes_out);
+int ysb_compute_tp(const void *d_gt, const int64_t *d_gt_offsets, int64_t total_gt, const void *d_pred,
+                   const int64_t *d_pred_offsets, int64_t total_pred, int batch, int is_f64, const double *iou_thresholds,
+                   void *d_workspace, size_t workspace_bytes, uint8_t *d_tp, void *stream);
 
 /* Soft-NMS (utils/nms.py:68-140; no caller in the reference, float32 GIoU/DIoU/CIoU flavours only -- 'iou' is broken
  * there).  Repeats: pick the first arg-max, record processed[idx] = its current score, decay every score whose IoU with

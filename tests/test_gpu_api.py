@@ -315,6 +315,102 @@ def test_undo_letterbox_bit_exact():
         pp.undo_letterbox(buf, [info])
 
 
+def test_fused_letterbox_undo_equals_separate_pass():
+    """ysb_params.d_letterbox: the undo of val_yolov5.py:166-172 inside the NMS kernel's row write == NMS rows mapped
+    afterwards by the oracle's literal restatement (bit-exact), per image, incl. TTA; counts and indices unchanged; and
+    the evaluator mirror's DetectionList lets preds_postprocess reuse the device rows."""
+    from yoloseries_b200 import synth
+    from yoloseries_b200.engine import DetectionList, PostProcessor, preds_postprocess
+    from yoloseries_b200.trainer import YOLOV5Evaluator
+    hyp = oracle.default_hyp(num_class=6, postprocess_bbox=False)
+    anchors = torch.tensor(synth.V5_ANCHORS_PX)
+    heads = synth.make_heads("yolov5", 3, 128, 160, 6, "crowd", seed=9, device="cuda")
+    infos = [dict(scale=0.731, pad_top=3, pad_left=0, org_shape=(167, 219)),
+             dict(scale=0.25, pad_top=0, pad_left=21, org_shape=(512, 470)),
+             dict(scale=1.0, pad_top=0, pad_left=0, org_shape=(128, 160))]
+    pp = PostProcessor("yolov5", hyp, anchors=anchors)
+    plain, plain_idx = pp.to_list(pp.run(heads, 128, 160), as_numpy=True, with_index=True)
+    fused, fused_idx = pp.to_list(pp.run(heads, 128, 160, info=infos), as_numpy=True, with_index=True)
+    again = pp.to_list(pp.run(heads, 128, 160), as_numpy=True)      # info=None switches it off again
+    assert sum(r.shape[0] for r in plain) > 30
+    for i, d in enumerate(infos):
+        want = oracle.undo_letterbox(plain[i], d["scale"], d["pad_top"], d["pad_left"], *d["org_shape"])
+        np.testing.assert_array_equal(fused[i], want)
+        np.testing.assert_array_equal(fused_idx[i], plain_idx[i])
+        np.testing.assert_array_equal(again[i], plain[i])
+    with pytest.raises(ValueError):
+        pp.run(heads, 128, 160, info=infos[:2])
+    # evaluator mirror: __call__(inputs, info=...) fused; __call__(inputs) + preds_postprocess(outputs, info) on device rows
+    hyp_e = dict(hyp, device="cuda", use_tta=False, input_img_size=[128, 160], wfb=False)
+    ev = YOLOV5Evaluator(lambda x: [h.clone() for h in heads], anchors, hyp_e)
+    x = torch.zeros(3, 3, 128, 160, device="cuda")
+    outs = ev(x)
+    assert isinstance(outs, DetectionList) and outs.device_rows is not None
+    mapped = preds_postprocess(outs, infos)
+    direct = ev(x, info=infos)
+    for i in range(3):
+        np.testing.assert_array_equal(outs[i].numpy(), plain[i])
+        np.testing.assert_array_equal(mapped[i], fused[i])
+        np.testing.assert_array_equal(direct[i].numpy(), fused[i])
+    # TTA: the undo applies to the merged result
+    hyp_t = dict(hyp_e, use_tta=True)
+    ev_t = YOLOV5Evaluator(lambda x: synth.make_heads("yolov5", 3, x.shape[2], x.shape[3], 6, "crowd", seed=9, device="cuda"),
+                           anchors, hyp_t)
+    base = ev_t(x)
+    got = ev_t(x, info=infos)
+    for i, d in enumerate(infos):
+        want = oracle.undo_letterbox(base[i].numpy(), d["scale"], d["pad_top"], d["pad_left"], *d["org_shape"])
+        np.testing.assert_array_equal(got[i].numpy(), want)
+
+
+def test_compute_tp_matches_reference():
+    """utils/mAP.py:18-42, 70-100 through ysb_map_iou / ysb_compute_tp: the reference's own tp matrices and IoUs
+    (utils_extra.npz, float32 and float64 images), one launch for the whole list, and random images vs the oracle."""
+    from yoloseries_b200.utils import compute_tp, compute_tp_batch
+    from yoloseries_b200.utils.mAP import iou as map_iou
+    g = load_golden("utils_extra")
+    gts, preds = [g[f"tp_gt_{i}"] for i in range(6)], [g[f"tp_pred_{i}"] for i in range(6)]
+    for i in range(6):
+        got = compute_tp(gts[i], preds[i])
+        assert got.dtype == bool and got.shape == (preds[i].shape[0], 10)
+        np.testing.assert_array_equal(got, g[f"tp_out_{i}"], err_msg=f"image {i}")
+        io = map_iou(gts[i][:, :4], preds[i][:, :4])
+        assert io.dtype == g[f"tp_iou_{i}"].dtype and io.shape == g[f"tp_iou_{i}"].shape
+        np.testing.assert_array_equal(io, g[f"tp_iou_{i}"])
+    # images of one precision batched into one launch
+    for sel in ([0, 1, 2, 4], [3, 5]):
+        outs = compute_tp_batch([gts[i] for i in sel], [preds[i] for i in sel])
+        for i, o in zip(sel, outs):
+            np.testing.assert_array_equal(o, g[f"tp_out_{i}"])
+    # mixed precisions promote to float64 like numpy: compare with the oracle on the promoted arrays
+    outs = compute_tp_batch(gts, preds)
+    for i, o in enumerate(outs):
+        np.testing.assert_array_equal(o, oracle.compute_tp(gts[i].astype(np.float64), preds[i].astype(np.float64)))
+    # a validation-sized run: 200 images x up to 300 kept rows
+    rng = np.random.default_rng(21)
+    big_g, big_p = [], []
+    for _ in range(200):
+        n = int(rng.integers(0, 40))
+        xy = rng.uniform(0, 600, size=(n, 2))
+        gt = np.concatenate((xy, xy + rng.uniform(10, 200, size=(n, 2)), rng.integers(0, 5, size=(n, 1))), axis=1).astype(np.float32)
+        m = int(rng.integers(0, 300))
+        src = gt[rng.integers(0, n, size=m)] if n else np.zeros((m, 5), np.float32)
+        box = src[:, :4] + rng.normal(0, 8, size=(m, 4)).astype(np.float32)
+        lab = np.where(rng.random(m) < 0.9, src[:, 4], rng.integers(0, 5, size=m)).astype(np.float32)
+        big_g.append(gt)
+        big_p.append(np.concatenate((box, rng.uniform(0, 1, size=(m, 1)).astype(np.float32), lab[:, None]), axis=1).astype(np.float32))
+    outs = compute_tp_batch(big_g, big_p)
+    total = 0
+    for gt, pr, o in zip(big_g, big_p, outs):
+        want = oracle.compute_tp(gt, pr)
+        np.testing.assert_array_equal(o, want)
+        total += int(want.sum())
+    assert total > 5000
+    assert compute_tp_batch([], []) == []
+    with pytest.raises(ValueError):
+        compute_tp_batch(gts, preds[:2])
+
+
 def test_gather_detections_single_process_identity():
     from yoloseries_b200.dist import gather_detections
     d = torch.rand(4, 10, 6, device="cuda")

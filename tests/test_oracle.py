@@ -239,3 +239,20 @@ def test_pairwise_iou_backward_matches_reference_autograd():
     g = load_golden("utils_extra")
     d1, d2 = oracle.pairwise_iou_backward(g["pair_b1"], g["pair_b2"], g["pair_w"])
     assert np.abs(d1 - g["pair_d1"]).max() <= 1e-7 and np.abs(d2 - g["pair_d2"]).max() <= 1e-7
+
+
+def test_compute_tp_matches_reference():
+    """oracle.compute_tp / map_iou vs the reference's mAP_v2.compute_tp / utils.mAP.iou (utils_extra.npz), bit-exact."""
+    g = load_golden("utils_extra")
+    np.testing.assert_array_equal(g["tp_thr"], oracle.evalside.IOU_THRESHOLDS)
+    seen = 0
+    for i in range(6):
+        gt, pred = g[f"tp_gt_{i}"], g[f"tp_pred_{i}"]
+        got = oracle.compute_tp(gt, pred)
+        assert got.dtype == bool and got.shape == (pred.shape[0], 10)
+        np.testing.assert_array_equal(got, g[f"tp_out_{i}"])
+        io = oracle.map_iou(gt[:, :4], pred[:, :4])
+        assert io.dtype == g[f"tp_iou_{i}"].dtype
+        np.testing.assert_array_equal(io, g[f"tp_iou_{i}"])
+        seen += int(got.sum())
+    assert seen > 100

@@ -24,7 +24,7 @@ IOU_NUMBA_F64MIX, IOU_F32, GIOU, DIOU, CIOU = range(5)
 IOU_KIND_IDS = {"numba": IOU_NUMBA_F64MIX, "iou": IOU_F32, "giou": GIOU, "diou": DIOU, "ciou": CIOU}
 CMP_GE, CMP_GT = 0, 1
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 YSB_MAX_PASSES = 4
 YSB_MAX_PEERS = 16
 YSB_IPC_HANDLE_BYTES = 64
@@ -64,6 +64,7 @@ class YsbParams(ctypes.Structure):
         ("tta_flip", ctypes.c_int32),
         ("tta_img_h", ctypes.c_int32),
         ("tta_img_w", ctypes.c_int32),
+        ("d_letterbox", ctypes.c_void_p),
     ]
 
 
@@ -128,6 +129,12 @@ _SIGNATURES = {
                                                     ctypes.c_void_p]),
     "ysb_pairwise_iou_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "ysb_map_iou": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
+                                   ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "ysb_compute_tp_workspace_bytes": (ctypes.c_int, [ctypes.c_int64, ctypes.POINTER(ctypes.c_size_t)]),
+    "ysb_compute_tp": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
+                                      ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
     "ysb_gather_buffer_bytes": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                ctypes.POINTER(ctypes.c_size_t)]),
     "ysb_gather_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]),

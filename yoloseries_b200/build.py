@@ -13,7 +13,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 OUT_DIR = os.path.join(PKG, "_lib")
 LIB = os.path.join(OUT_DIR, "libysb_postproc.so")
-SOURCES = ["c_abi.cu", "filter_kernels.cu", "nms_kernel.cu", "decode_kernels.cu", "iou_kernels.cu", "gather_kernels.cu"]
+SOURCES = ["c_abi.cu", "filter_kernels.cu", "nms_kernel.cu", "decode_kernels.cu", "iou_kernels.cu", "gather_kernels.cu", "eval_kernels.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

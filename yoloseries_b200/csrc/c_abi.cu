@@ -36,6 +36,10 @@ void debug_set_nms_threads(int t);
 
 cudaError_t launch_elementwise_iou_backward(const float *b1, int64_t n1, const float *b2, int64_t n2, int kind,
                                             const float *grad_out, float *g1, float *g2, cudaStream_t stream);
+cudaError_t launch_map_iou(const void *b1, int64_t n, int w1, const void *b2, int64_t m, int w2, int f64, void *out,
+                           cudaStream_t stream);
+cudaError_t launch_compute_tp(const void *gt, const int64_t *gt_off, const void *pred, const int64_t *pred_off, int batch,
+                              int f64, const double *thr10, int32_t *first_pred, uint8_t *tp, cudaStream_t stream);
 cudaError_t launch_pairwise_iou_backward(const float *b1, int64_t n, const float *b2, int64_t m, const float *grad_out,
                                          float *g1, float *g2, cudaStream_t stream);
 cudaError_t launch_soft_nms(const float *boxes, const float *scores, int64_t m, float thr, int kind, int mode, float sigma,
@@ -121,6 +125,7 @@ static int build_plan(const ysb_params *p, const void *const *d_heads, int num_h
     P.tta_flip = p->tta_flip;
     P.tta_h = static_cast<float>(p->tta_img_h);
     P.tta_w = static_cast<float>(p->tta_img_w);
+    P.letterbox = p->d_letterbox;
 
     int64_t n = 0;
     for (int l = 0; l < L; ++l) {
@@ -608,6 +613,38 @@ int ysb_pairwise_iou_backward(const float *d_b1, int64_t n, const float *d_b2, i
     if (n > 0x7fffffffll) return YSB_ERR_LIMIT;
     return cuda_status(launch_pairwise_iou_backward(d_b1, n, d_b2, m, d_grad_out, d_grad_b1, d_grad_b2,
                                                     static_cast<cudaStream_t>(stream)));
+}
+
+int ysb_map_iou(const void *d_box1, int64_t n, int row_w1, const void *d_box2, int64_t m, int row_w2, int is_f64,
+                void *d_out, void *stream)
+{
+    if (n < 0 || m < 0 || row_w1 < 4 || row_w2 < 4) return YSB_ERR_BAD_ARG;
+    if (n > 0 && m > 0 && (!d_box1 || !d_box2 || !d_out)) return YSB_ERR_BAD_ARG;
+    return cuda_status(launch_map_iou(d_box1, n, row_w1, d_box2, m, row_w2, is_f64 != 0, d_out,
+                                      static_cast<cudaStream_t>(stream)));
+}
+
+int ysb_compute_tp_workspace_bytes(int64_t total_gt, size_t *bytes_out)
+{
+    if (total_gt < 0 || !bytes_out) return YSB_ERR_BAD_ARG;
+    *bytes_out = sizeof(int32_t) * static_cast<size_t>(total_gt > 0 ? total_gt : 1);
+    return YSB_OK;
+}
+
+int ysb_compute_tp(const void *d_gt, const int64_t *d_gt_offsets, int64_t total_gt, const void *d_pred,
+                   const int64_t *d_pred_offsets, int64_t total_pred, int batch, int is_f64, const double *iou_thresholds,
+                   void *d_workspace, size_t workspace_bytes, uint8_t *d_tp, void *stream)
+{
+    if (batch < 0 || total_gt < 0 || total_pred < 0 || !iou_thresholds) return YSB_ERR_BAD_ARG;
+    if (batch > 0 && (!d_gt_offsets || !d_pred_offsets)) return YSB_ERR_BAD_ARG;
+    if ((total_gt > 0 && !d_gt) || (total_pred > 0 && (!d_pred || !d_tp))) return YSB_ERR_BAD_ARG;
+    if (total_gt > 0x7fffffffll || total_pred > 0x7fffffffll / 10) return YSB_ERR_LIMIT;
+    if (total_gt > 0 && (!d_workspace || workspace_bytes < sizeof(int32_t) * static_cast<size_t>(total_gt)))
+        return YSB_ERR_WORKSPACE;
+    for (int t = 0; t < 10; ++t)
+        if (!(iou_thresholds[t] == iou_thresholds[t])) return YSB_ERR_BAD_ARG;
+    return cuda_status(launch_compute_tp(d_gt, d_gt_offsets, d_pred, d_pred_offsets, batch, is_f64 != 0, iou_thresholds,
+                                         static_cast<int32_t *>(d_workspace), d_tp, static_cast<cudaStream_t>(stream)));
 }
 
 int ysb_soft_nms(const float *d_boxes, const float *d_scores, int64_t m, float iou_thr, int iou_kind, int mode,

@@ -833,6 +833,17 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
     __syncthreads();
     K2_STAMP(5);
     // ---- ordered write of the surviving rows ---------------------------------------------------------------
+    // optional letterbox undo (val_yolov5.py:166-172) on the way out: the filters above saw the un-mapped boxes
+    float lb_scale = 1.0f, lb_top = 0.0f, lb_left = 0.0f, lb_hi_y = 0.0f, lb_hi_x = 0.0f;
+    const bool lb = !ARRAY && P.letterbox != nullptr;
+    if (lb) {
+        const float *t = P.letterbox + static_cast<size_t>(img) * 5;
+        lb_scale = __ldg(t);
+        lb_top = __ldg(t + 1);
+        lb_left = __ldg(t + 2);
+        lb_hi_y = __fsub_rn(__ldg(t + 3), 1.0f);
+        lb_hi_x = __fsub_rn(__ldg(t + 4), 1.0f);
+    }
     int written = 0;
     for (int r0 = 0; r0 < kept; r0 += THREADS) {
         const int r = r0 + tid;
@@ -861,6 +872,12 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
             const float sc = key_score(key);
             const float s_out = P.topk_sqrt ? sqrtf(sc) : sc;  // FCOS: x[:, 4] = sqrt(x[:, 4]) (trainer/eval_fcos.py:281)
             const float c_out = static_cast<float>(key_cls(key));
+            if (lb) {
+                box.x = fminf(fmaxf(__fdiv_rn(__fsub_rn(box.x, lb_left), lb_scale), 1.0f), lb_hi_x);
+                box.z = fminf(fmaxf(__fdiv_rn(__fsub_rn(box.z, lb_left), lb_scale), 1.0f), lb_hi_x);
+                box.y = fminf(fmaxf(__fdiv_rn(__fsub_rn(box.y, lb_top), lb_scale), 1.0f), lb_hi_y);
+                box.w = fminf(fmaxf(__fdiv_rn(__fsub_rn(box.w, lb_top), lb_scale), 1.0f), lb_hi_y);
+            }
             const size_t off = (static_cast<size_t>(img) * max_det + at) * 6;
             // one destination (the caller's buffer) or, in a detection gather, every rank's receive slot: plain stores,
             // local or over NVLink; a warp writes 32 consecutive rows = 768 contiguous bytes

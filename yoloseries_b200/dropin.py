@@ -5,12 +5,15 @@
 
 Evaluators bind ``numba_nms`` & co. at import time (``from utils import ...``, trainer/eval_yolov5.py:4-7), so both the
 ``utils`` attributes and the already-bound names inside ``trainer.eval_*`` are replaced.
-Loss modules keep the reference's differentiable torch IoUs: only the post-processing seam is patched.
+``mAP_v2.compute_tp`` (utils/mAP.py:70-100) is rebound as well.  Loss modules keep the reference's torch IoUs unless
+``patch_iou=True``: then gpu_iou / gpu_Giou / gpu_DIoU / gpu_CIoU are replaced too, in ``utils``, ``utils.bbox_tools`` and
+every imported ``loss.*`` module that bound them (the mirrors are differentiable: ysb_*_iou_backward).
 """
 import sys
 
 from . import trainer as _trainer
 from .utils import bbox_tools as _bbox
+from .utils import mAP as _map
 from .utils import nms as _nms
 
 _EVALUATORS = {
@@ -20,7 +23,7 @@ _EVALUATORS = {
 }
 
 
-def install(patch_evaluators=True, patch_utils=True):
+def install(patch_evaluators=True, patch_utils=True, patch_iou=False):
     """Returns the list of names that were replaced."""
     done = []
     ref_utils, ref_trainer = sys.modules.get("utils"), sys.modules.get("trainer")
@@ -37,6 +40,19 @@ def install(patch_evaluators=True, patch_utils=True):
                     setattr(mod, name, fn)
             for modname in _EVALUATORS:
                 mod = sys.modules.get(f"trainer.{modname}")
+                if mod is not None and hasattr(mod, name):
+                    setattr(mod, name, fn)
+            done.append(f"utils.{name}")
+        ref_map = getattr(ref_utils, "mAP_v2", None)
+        if ref_map is not None and hasattr(ref_map, "compute_tp"):
+            ref_map.compute_tp = _map._compute_tp_method
+            done.append("utils.mAP_v2.compute_tp")
+    if patch_iou:
+        for name in ("gpu_iou", "gpu_Giou", "gpu_DIoU", "gpu_CIoU"):
+            fn = getattr(_bbox, name)
+            holders = [ref_utils, sys.modules.get("utils.bbox_tools")]
+            holders += [m for k, m in list(sys.modules.items()) if k == "loss" or k.startswith("loss.")]
+            for mod in holders:
                 if mod is not None and hasattr(mod, name):
                     setattr(mod, name, fn)
             done.append(f"utils.{name}")

@@ -159,11 +159,21 @@ def letterbox_table(info):
              float(d["org_shape"][1])] for d in info]
 
 
+class DetectionList(list):
+    """The evaluator's output list (CPU rows, the reference's contract) that also remembers the device rows it was read
+    from, so that preds_postprocess can map them without staging them back to the GPU."""
+    device_rows = None    # (b, max_det, 6) float32 CUDA tensor (a private copy, not the reused output buffer)
+    device_cnt = None     # (b,) int32 CUDA tensor
+
+
 def preds_postprocess(outputs, info):
     """val_yolov5.py:164-177 for an evaluator's output list: list[Tensor(K,6) | None] -> list[ndarray(K,6) | None].
 
     (The image half of the reference's method -- un-padding and resizing the input picture for drawing -- is
-    visualisation and stays with the caller.)  Rows are staged to the device, mapped by ysb_undo_letterbox, and read back.
+    visualisation and stays with the caller.)  When ``outputs`` is the DetectionList an evaluator mirror returned, the
+    rows are still on the device: ysb_undo_letterbox runs on them and only the mapped rows come back.  Any other list is
+    staged to the device first.  (Callers that pass ``info`` to the evaluator get the undo fused into the NMS kernel's
+    row write and need neither.)
     """
     if len(outputs) != len(info):
         raise ValueError(f"need one info dict per image: {len(info)} != {len(outputs)}")
@@ -172,19 +182,26 @@ def preds_postprocess(outputs, info):
     if not torch.cuda.is_available():
         raise RuntimeError("yoloseries_b200 needs a CUDA device: the engine has no CPU fallback")
     lib = _lib.load()
-    dev = torch.device("cuda", torch.cuda.current_device())
-    kmax = max([1] + [int(o.shape[0]) for o in outputs if o is not None])
-    host = torch.zeros((len(outputs), kmax, 6), dtype=torch.float32)
-    cnt = torch.tensor([(-1 if o is None else int(o.shape[0])) for o in outputs], dtype=torch.int32)
-    for i, o in enumerate(outputs):
-        if o is not None and o.shape[0]:
-            host[i, : o.shape[0]] = torch.as_tensor(o, dtype=torch.float32).reshape(-1, 6)
-    dets, dcnt = host.to(dev), cnt.to(dev)
+    if isinstance(outputs, DetectionList) and outputs.device_rows is not None:
+        dets, dcnt = outputs.device_rows.clone(), outputs.device_cnt
+        dev = dets.device
+        cnt = [(-1 if o is None else int(o.shape[0])) for o in outputs]
+        kmax = dets.shape[1]
+    else:
+        dev = torch.device("cuda", torch.cuda.current_device())
+        kmax = max([1] + [int(o.shape[0]) for o in outputs if o is not None])
+        host = torch.zeros((len(outputs), kmax, 6), dtype=torch.float32)
+        cnt = [(-1 if o is None else int(o.shape[0])) for o in outputs]
+        for i, o in enumerate(outputs):
+            if o is not None and o.shape[0]:
+                host[i, : o.shape[0]] = torch.as_tensor(o, dtype=torch.float32).reshape(-1, 6)
+        dets, dcnt = host.to(dev), torch.tensor(cnt, dtype=torch.int32).to(dev)
     table = torch.tensor(letterbox_table(info), dtype=torch.float32).to(dev)
-    _lib.check(lib.ysb_undo_letterbox(dets.data_ptr(), dcnt.data_ptr(), len(outputs), kmax, table.data_ptr(),
-                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "ysb_undo_letterbox")
-    back = dets.cpu().numpy()
-    return [None if c < 0 else back[i, :c].copy() for i, c in enumerate(cnt.tolist())]
+    with torch.cuda.device(dev):
+        _lib.check(lib.ysb_undo_letterbox(dets.data_ptr(), dcnt.data_ptr(), len(outputs), kmax, table.data_ptr(),
+                                          ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "ysb_undo_letterbox")
+    back = dets[:, : max(max(cnt), 1)].cpu().numpy()
+    return [None if c < 0 else back[i, :c].copy() for i, c in enumerate(cnt)]
 
 
 def validate_heads(family, flat, num_class, anchors=None, dfl_bins=16, decoded_row_w=None):
@@ -335,8 +352,23 @@ class PostProcessor:
                                             self._stream(dev)), "ysb_decode")
         return out
 
-    def run(self, heads, img_h, img_w, decoded=False):
-        """Whole path on the device.  Returns DetectionBuffers (views into reused storage)."""
+    def _letterbox(self, holder, params_list, info, batch, dev):
+        """Stage the reference's per-image info dicts as the (b, 5) table the NMS kernel's row write reads (fused
+        preds_postprocess, val_yolov5.py:166-172); ``info`` None switches the undo off."""
+        ptr = None
+        if info is not None:
+            if len(info) != batch:
+                raise ValueError(f"need one info dict per image: {len(info)} != {batch}")
+            if "lb" not in holder:
+                holder["lb"] = torch.empty((batch, 5), dtype=torch.float32, device=dev)
+            holder["lb"].copy_(torch.tensor(letterbox_table(info), dtype=torch.float32), non_blocking=False)
+            ptr = holder["lb"].data_ptr()
+        for p in params_list:
+            p.d_letterbox = ptr
+
+    def run(self, heads, img_h, img_w, decoded=False, info=None):
+        """Whole path on the device.  Returns DetectionBuffers (views into reused storage).  ``info``: optional list of
+        the reference's letterbox dicts (scale, pad_top, pad_left, org_shape): rows come out in original-picture pixels."""
         flat = [heads] if decoded else flatten_heads(self.family, heads)
         batch = flat[0].shape[0]
         if batch == 0:  # the reference loops over zero images and returns []
@@ -348,6 +380,7 @@ class PostProcessor:
         ws = ent["workspace"]
         dev = flat[0].device
         with torch.cuda.device(dev):   # kernels, function attributes and the stream all belong to the heads' device
+            self._letterbox(ent, [ent["params"]], info, batch, dev)
             _lib.check(self._lib.ysb_postprocess(ctypes.byref(ent["params"]), ptrs, len(flat), ws.data_ptr(), ws.numel(),
                                                  out.dets.data_ptr(), out.det_idx.data_ptr(), out.det_cnt.data_ptr(),
                                                  self._stream(dev)), "ysb_postprocess")
@@ -383,7 +416,7 @@ class PostProcessor:
             off += ent["N"]
         return out, views
 
-    def run_tta(self, passes, org_hw):
+    def run_tta(self, passes, org_hw, info=None):
         """The whole path over several augmented passes without the merged tensor (ysb_postprocess_tta).  Candidate
         indices (det_idx) count through the passes in order, like rows of the reference's concatenated tensor."""
         ents = self._tta_entries(passes, org_hw)
@@ -406,6 +439,7 @@ class PostProcessor:
         per_pass = (ctypes.c_int32 * n)(*[len(flat) for flat, _ in ents])
         out, ws = bundle["out"], bundle["workspace"]
         with torch.cuda.device(dev):
+            self._letterbox(bundle, [bundle["params"][i] for i in range(n)], info, batch, dev)
             _lib.check(self._lib.ysb_postprocess_tta(bundle["params"], n, _lib.head_pointer_array(flat_all), per_pass,
                                                      ws.data_ptr(), ws.numel(), out.dets.data_ptr(), out.det_idx.data_ptr(),
                                                      out.det_cnt.data_ptr(), self._stream(dev)), "ysb_postprocess_tta")
@@ -486,6 +520,9 @@ class PostProcessor:
             res.append(r.numpy() if as_numpy else r)
             if with_index:
                 ids.append(idx[i, :c].clone().numpy())
+        if not with_index and not as_numpy:
+            res = DetectionList(res)
+            res.device_rows, res.device_cnt = out.dets[:, : max(kmax, 1)].clone(), out.det_cnt.clone()
         return (res, ids) if with_index else res
 
 

@@ -42,15 +42,18 @@ class _Evaluator:
 
     # ---- reference API -------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def __call__(self, inputs):
+    def __call__(self, inputs, info=None):
+        """``info`` (extension, default None = the reference's behaviour): the per-image letterbox dicts val_*.py hands to
+        preds_postprocess; when given, the undo is fused into the NMS kernel's row write and the rows come back in
+        original-picture pixels."""
         if self.use_tta:
             if self.hyp.get("wfb", False):
                 raise NotImplementedError("weighted-box-fusion (hyp['wfb']) is a 'next' row (SURVEY.md 8f rank 3)")
             # three model forwards, then ONE fused call: no decoded or merged tensor is written (ysb_postprocess_tta)
-            out = self._pp.run_tta(self._tta_passes(inputs), (inputs.size(2), inputs.size(3)))
+            out = self._pp.run_tta(self._tta_passes(inputs), (inputs.size(2), inputs.size(3)), info=info)
             return self._pp.to_list(out)
         heads = normalise_heads(self._model(inputs))
-        out = self._pp.run(heads, inputs.size(2), inputs.size(3))
+        out = self._pp.run(heads, inputs.size(2), inputs.size(3), info=info)
         return self._pp.to_list(out)
 
     @torch.no_grad()
