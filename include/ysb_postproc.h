@@ -213,6 +213,12 @@ int ysb_elementwise_iou_backward(const float *d_b1, int64_t n1, const float *d_b
 int ysb_pairwise_iou_backward(const float *d_b1, int64_t n, const float *d_b2, int64_t m, const float *d_grad_out,
                               float *d_grad_b1, float *d_grad_b2, void *stream);
 
+/* Self-test of the arithmetic the parity claims rest on: the sigmoid's reciprocal is spelled out (MUFU.RCP + one FMA
+ * Newton step) instead of calling __frcp_rn; this compares the two for every float in [1, +inf] on the device.
+ * d_mismatches (2) uint64: {values where the guarded routine differs, values where the branch-free batch variant differs
+ * or mis-flags its out-of-range case}.  Both must come back 0. */
+int ysb_selftest_reciprocal(uint64_t *d_mismatches, void *stream);
+
 /* mAP hand-off (the consumer of the kept rows, val_yolov5.py:388 -> utils/mAP.py).
  * ysb_map_iou: utils/mAP.py:18-42 `iou(box1, box2)` -- rows of row_w1 / row_w2 values whose first four are
  * (x1, y1, x2, y2); float32 or float64 (is_f64) in, the same type out, (n, m);  inter / clip(a1 + a2 - inter, 1e-6, 1e7).

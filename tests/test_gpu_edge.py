@@ -277,7 +277,7 @@ def test_filter_kernel_variants_emit_the_same_survivors():
     import subprocess
     import sys
     from yoloseries_b200 import build as ysb_build
-    have_variants = os.path.exists(ysb_build.VARIANTS_LIB)
+    have_variants = ysb_build.variants_fresh()   # a stale profiling build (older ABI) is not used
     child = r'''
 import hashlib, sys, torch
 sys.path.insert(0, ".")
@@ -335,3 +335,15 @@ def test_boxes_wider_than_the_class_offset():
             if w.rows is not None:
                 np.testing.assert_array_equal(rows[i], w.rows)
                 np.testing.assert_array_equal(idx[i], w.cand_index)
+
+
+def test_sigmoid_reciprocal_is_frcp_rn():
+    """sigmoid_ref's spelled-out reciprocal == __frcp_rn for every float in [1, +inf] (1.07e9 bit patterns), and the
+    branch-free batch variant of the decode kernel agrees below 2^126 and flags everything at or above it."""
+    import ctypes
+
+    from yoloseries_b200 import _lib
+    bad = torch.full((2,), -1, dtype=torch.int64, device="cuda")
+    _lib.check(_lib.load().ysb_selftest_reciprocal(bad.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+               "ysb_selftest_reciprocal")
+    assert bad.tolist() == [0, 0]

@@ -21,15 +21,21 @@ FLAGS = [
 ]
 
 
-def _stale():
-    if not os.path.exists(LIB):
+def _stale(lib=None):
+    lib = lib or LIB
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "ysb_postproc.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 VARIANTS_LIB = os.path.join(OUT_DIR, "libysb_postproc_variants.so")
+
+
+def variants_fresh():
+    """True when the profiling build exists and is at least as new as every source it was built from."""
+    return not _stale(VARIANTS_LIB)
 
 
 def build_variants(verbose=False):

@@ -36,6 +36,7 @@ void debug_set_nms_threads(int t);
 
 cudaError_t launch_elementwise_iou_backward(const float *b1, int64_t n1, const float *b2, int64_t n2, int kind,
                                             const float *grad_out, float *g1, float *g2, cudaStream_t stream);
+cudaError_t launch_selftest_reciprocal(unsigned long long *d_mismatches, cudaStream_t stream);
 cudaError_t launch_map_iou(const void *b1, int64_t n, int w1, const void *b2, int64_t m, int w2, int f64, void *out,
                            cudaStream_t stream);
 cudaError_t launch_compute_tp(const void *gt, const int64_t *gt_off, const void *pred, const int64_t *pred_off, int batch,
@@ -613,6 +614,13 @@ int ysb_pairwise_iou_backward(const float *d_b1, int64_t n, const float *d_b2, i
     if (n > 0x7fffffffll) return YSB_ERR_LIMIT;
     return cuda_status(launch_pairwise_iou_backward(d_b1, n, d_b2, m, d_grad_out, d_grad_b1, d_grad_b2,
                                                     static_cast<cudaStream_t>(stream)));
+}
+
+int ysb_selftest_reciprocal(uint64_t *d_mismatches, void *stream)
+{
+    if (!d_mismatches) return YSB_ERR_BAD_ARG;
+    return cuda_status(launch_selftest_reciprocal(reinterpret_cast<unsigned long long *>(d_mismatches),
+                                                  static_cast<cudaStream_t>(stream)));
 }
 
 int ysb_map_iou(const void *d_box1, int64_t n, int row_w1, const void *d_box2, int64_t m, int row_w2, int is_f64,

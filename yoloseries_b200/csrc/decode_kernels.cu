@@ -12,8 +12,14 @@
 
 namespace ysb {
 
-constexpr int kDecRows = 32;
 constexpr int kDecThreads = 256;
+// Independent class-logit loads a thread issues before its first sigmoid.  The kernel is bound by memory-level
+// parallelism: measured on B200, 64 YOLOv5s images (profiles/r2_decode_bench.txt): 4 in flight 0.330 ms, 10: 0.240 ms,
+// 20: 0.217 ms for the planes layout (80 classes = 2 phases x 2 batches of 20); channels-last rows have 8 threads per row,
+// i.e. 10 classes per thread at C = 80, and are fastest with exactly that batch (0.270 ms; 20 would always take the
+// bounds-checked tail).
+constexpr int kDecInFlight = 20;
+constexpr int kDecInFlightRows = 10;
 
 // Address of class logit 0 of a candidate and the stride between consecutive classes (hoisted out of the class loop:
 // the level lookup and the two integer divisions are per candidate, not per element).
@@ -59,25 +65,40 @@ __global__ void __launch_bounds__(kDecThreads) k_decode_rows(const __grid_consta
     const int rw = P.row_w;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (P.layout == LAYOUT_PLANES) {
-        // thread = (candidate, class phase): consecutive threads take consecutive positions of one plane; four
-        // independent loads in flight per thread, then four sigmoids
+        // thread = (candidate, class phase): consecutive threads take consecutive positions of one plane
         constexpr int kPhases = kDecThreads / ROWS;  // 2 for ROWS = 128
         const int rr = threadIdx.x % ROWS, ph = threadIdx.x / ROWS;
         if (rr < nrows) {
             const CandAddr ca = cand_addr(P, img, c0 + rr);
             float *tc = tile + rr * rw + P.cls_col;
             const size_t step = static_cast<size_t>(kPhases) * ca.cstride;
+            // kDecInFlight independent loads per thread before the first sigmoid: the kernel is bound by memory-level
+            // parallelism, not by instruction issue (4 loads in flight left DRAM at 37 % of peak)
+            const float ov = (ph == 0 && ca.obj) ? __ldg(ca.obj) : 0.0f;
+            const float *src = ca.cls + static_cast<size_t>(ph) * ca.cstride;
             int k = ph;
-            const float *src = ca.cls + static_cast<size_t>(k) * ca.cstride;
-            for (; k + 3 * kPhases < P.C; k += 4 * kPhases, src += 4 * step) {
-                const float v0 = __ldg(src), v1 = __ldg(src + step), v2 = __ldg(src + 2 * step), v3 = __ldg(src + 3 * step);
-                tc[k] = sigmoid_ref(v0);
-                tc[k + kPhases] = sigmoid_ref(v1);
-                tc[k + 2 * kPhases] = sigmoid_ref(v2);
-                tc[k + 3 * kPhases] = sigmoid_ref(v3);
+            // whole batches need no per-load bounds test (80 classes: four of them)
+            for (; k + (kDecInFlight - 1) * kPhases < P.C; k += kDecInFlight * kPhases, src += kDecInFlight * step) {
+                float v[kDecInFlight];
+#pragma unroll
+                for (int u = 0; u < kDecInFlight; ++u) v[u] = __ldg(src + u * step);
+                bool redo = false;
+#pragma unroll
+                for (int u = 0; u < kDecInFlight; ++u) tc[k + u * kPhases] = sigmoid_fast(v[u], redo);
+                if (__builtin_expect(redo, 0)) {   // a logit below -87.3: denormal sigmoid, library reciprocal
+#pragma unroll
+                    for (int u = 0; u < kDecInFlight; ++u) tc[k + u * kPhases] = sigmoid_ref(v[u]);
+                }
             }
-            for (; k < P.C; k += kPhases, src += step) tc[k] = sigmoid_ref(__ldg(src));
-            if (ph == 0 && ca.obj) tile[rr * rw + P.obj_col] = sigmoid_ref(__ldg(ca.obj));
+            if (k < P.C) {
+                float v[kDecInFlight];
+#pragma unroll
+                for (int u = 0; u < kDecInFlight; ++u) v[u] = (k + u * kPhases < P.C) ? __ldg(src + u * step) : 0.0f;
+#pragma unroll
+                for (int u = 0; u < kDecInFlight; ++u)
+                    if (k + u * kPhases < P.C) tc[k + u * kPhases] = sigmoid_ref(v[u]);
+            }
+            if (ph == 0 && ca.obj) tile[rr * rw + P.obj_col] = sigmoid_ref(ov);
         }
         if (P.family == YSB_YOLOV8) {
             // DFL boxes: four threads per candidate (one side each), 64 candidates per round
@@ -102,20 +123,32 @@ __global__ void __launch_bounds__(kDecThreads) k_decode_rows(const __grid_consta
         }
     } else {
         // eight threads per candidate row (32 rows x 8): a warp reads 4 rows x 32 contiguous bytes per step, every
-        // fetched sector fully used; four loads in flight per thread.  Lane-per-candidate box / objectness decode.
+        // fetched sector fully used; kDecInFlightRows loads in flight per thread.  Lane-per-candidate box / objectness decode.
         const int r = threadIdx.x >> 3, q = threadIdx.x & 7;
         if (r < nrows) {
             const CandAddr ca = cand_addr(P, img, c0 + r);
             float *tc = tile + r * rw + P.cls_col;
             int k = q;
-            for (; k + 24 < P.C; k += 32) {
-                const float v0 = __ldg(ca.cls + k), v1 = __ldg(ca.cls + k + 8), v2 = __ldg(ca.cls + k + 16), v3 = __ldg(ca.cls + k + 24);
-                tc[k] = sigmoid_ref(v0);
-                tc[k + 8] = sigmoid_ref(v1);
-                tc[k + 16] = sigmoid_ref(v2);
-                tc[k + 24] = sigmoid_ref(v3);
+            for (; k + 8 * (kDecInFlightRows - 1) < P.C; k += 8 * kDecInFlightRows) {
+                float v[kDecInFlightRows];
+#pragma unroll
+                for (int u = 0; u < kDecInFlightRows; ++u) v[u] = __ldg(ca.cls + k + 8 * u);
+                bool redo = false;
+#pragma unroll
+                for (int u = 0; u < kDecInFlightRows; ++u) tc[k + 8 * u] = sigmoid_fast(v[u], redo);
+                if (__builtin_expect(redo, 0)) {
+#pragma unroll
+                    for (int u = 0; u < kDecInFlightRows; ++u) tc[k + 8 * u] = sigmoid_ref(v[u]);
+                }
             }
-            for (; k < P.C; k += 8) tc[k] = sigmoid_ref(__ldg(ca.cls + k));
+            if (k < P.C) {
+                float v[kDecInFlightRows];
+#pragma unroll
+                for (int u = 0; u < kDecInFlightRows; ++u) v[u] = (k + 8 * u < P.C) ? __ldg(ca.cls + k + 8 * u) : 0.0f;
+#pragma unroll
+                for (int u = 0; u < kDecInFlightRows; ++u)
+                    if (k + 8 * u < P.C) tc[k + 8 * u] = sigmoid_ref(v[u]);
+            }
         }
         if (warp == 0 && lane < nrows) {
             const int cand = c0 + lane;
@@ -162,6 +195,38 @@ cudaError_t launch_decode(const Plan &P, float *d_out, int64_t rows_total, int64
     if (P.layout == LAYOUT_PLANES && static_cast<size_t>(128) * P.row_w * sizeof(float) <= 100 * 1024)
         return launch_decode_t<128>(P, d_out, rows_total, row_offset, stream);
     return launch_decode_t<32>(P, d_out, rows_total, row_offset, stream);
+}
+
+// Self-test: the spelled-out reciprocal of sigmoid_ref / sigmoid_fast against __frcp_rn for EVERY float in [1, +inf]
+// (bit patterns 0x3f800000 .. 0x7f800000, 1.07e9 values).  mismatches[0] += values where rcp_rn_ge1 differs,
+// mismatches[1] += values below 2^126 where the branch-free fast path differs or flags a redo, or at / above 2^126 where
+// it fails to flag one.
+__global__ void __launch_bounds__(256) k_selftest_reciprocal(unsigned long long *__restrict__ mismatches)
+{
+    const uint32_t lo = 0x3f800000u, hi = 0x7f800000u;
+    unsigned long long bad0 = 0, bad1 = 0;
+    for (uint64_t b = lo + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; b <= hi;
+         b += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const float d = __uint_as_float(static_cast<uint32_t>(b));
+        const uint32_t want = __float_as_uint(__frcp_rn(d));
+        if (__float_as_uint(rcp_rn_ge1(d)) != want) ++bad0;
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+        const float e = __fmaf_rn(d, r, -1.0f);
+        const uint32_t fast = __float_as_uint(__fmaf_rn(r, -e, r));
+        const bool redo = d >= 8.507059173e37f;
+        if (redo != (b >= 0x7e800000u) || (!redo && fast != want)) ++bad1;
+    }
+    if (bad0) atomicAdd(mismatches, bad0);
+    if (bad1) atomicAdd(mismatches + 1, bad1);
+}
+
+cudaError_t launch_selftest_reciprocal(unsigned long long *d_mismatches, cudaStream_t stream)
+{
+    cudaError_t e = cudaMemsetAsync(d_mismatches, 0, 2 * sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
+    k_selftest_reciprocal<<<148 * 8, 256, 0, stream>>>(d_mismatches);
+    return cudaGetLastError();
 }
 
 }  // namespace ysb
