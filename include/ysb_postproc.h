@@ -20,6 +20,7 @@
  *   ysb_pairwise_iou_backward     autograd of utils.gpu_iou  loss/yolox_loss.py:133, loss/yolov7_loss.py:312
  *   ysb_soft_nms          utils.gpu_*_soft_nms             utils/nms.py:68-140
  *   ysb_undo_letterbox    box half of preds_postprocess    val_yolov5.py:166-172
+ *   ysb_wbf, ysb_wbf_collect  weighted_fusion_bbox / do_wfb   utils/weighted_fusion_bbox.py:41-96, trainer/eval_yolov5.py:44-92
  *   ysb_map_iou           utils.mAP.iou                    utils/mAP.py:18-42
  *   ysb_compute_tp        mAP_v2.compute_tp                utils/mAP.py:70-100
  *   ysb_nms               utils.numba_nms / utils.gpu_nms  utils/nms.py:10-27 / 30-65
@@ -212,6 +213,36 @@ int ysb_elementwise_iou_backward(const float *d_b1, int64_t n1, const float *d_b
  * results).  Either gradient pointer may be NULL.  All box / gradient pointers 16-byte aligned. */
 int ysb_pairwise_iou_backward(const float *d_b1, int64_t n, const float *d_b2, int64_t m, const float *d_grad_out,
                               float *d_grad_b1, float *d_grad_b2, void *stream);
+
+/* Weighted-box-fusion (hyp['wfb'], utils/weighted_fusion_bbox.py:63-96 + update_fusion_bbox :41-60; caller
+ * trainer/eval_yolov5.py:44-92 do_wfb, identical in eval_yolov7.py / eval_yolox.py).
+ * ysb_wbf: d_rows (batch, stride, row_width) float32 rows (x1, y1, x2, y2, score, label, weight[, position]); image i
+ * holds d_counts[i] <= stride rows.  row_width 8: column 7 carries, as uint32 bits, the row's position in the reference's
+ * stacked list (rows may then be stored in any order); row_width 7: storage order is that position.  Per image and label
+ * (ascending), boxes are visited by descending score (equal scores: the later row first -- argsort()[::-1] of a stable
+ * sort; numpy's default sort is only stable up to 16 elements, unpinned beyond); a box joins every cluster whose fused
+ * box it meets with cpu_iou >= iou_thr (float32 box area, float64 otherwise, utils/bbox_tools.py:63-84), else it founds
+ * one; fused box = mean over members of box*score/sum(score) -- i.e. the score-weighted mean divided by the member
+ * count AGAIN, the reference's arithmetic, kept --, fused score = sum(score*weight)/sum(weight).  float64; cluster sums
+ * are kept incrementally (the reference re-sums every cluster after every box: values agree to ~1e-15 relative).
+ * Outputs, all (batch, stride[, .]): d_order int32 = row visited at every sorted position; the clusters of a label occupy
+ * consecutive slots from the label's first sorted position: d_members int32 = member count (0 = no cluster in this
+ * slot), d_fusion float64 (.., 6) = (x1, y1, x2, y2, score, label).  d_pairs (pair_capacity, 2) int32 + d_pair_count (1)
+ * uint64, both optional: (cluster slot, sorted position) of every membership as indices into the flattened
+ * (batch * stride) arrays, unordered; the count may exceed the
+ * capacity (call again with more).  d_status (batch) int32: 1 = the best box of some label does not meet itself
+ * (degenerate box; the reference raises IndexError there).
+ * ysb_wbf_collect: do_wfb's per-pass filter on the decoded (batch, rows, 5 + C) tensor of all passes (xywh, obj, C class
+ * scores; pass q owns pass_rows[q] consecutive rows and weight pass_weights[q], HOST arrays): obj > skip_thr, conf =
+ * cls * obj, best class with conf > skip_thr (multi_label: every class above it), xywh -> xyxy -> d_records
+ * (batch, capacity, 8) rows as above with positions, d_counts (batch).  Survivors beyond capacity are counted, not stored. */
+int ysb_wbf_workspace_bytes(int batch, int64_t stride, size_t *bytes_out);
+int ysb_wbf(const float *d_rows, int row_width, const int32_t *d_counts, int batch, int64_t stride, double iou_thr,
+            void *d_workspace, size_t workspace_bytes, int32_t *d_order, double *d_fusion, int32_t *d_members,
+            int32_t *d_pairs, int64_t pair_capacity, uint64_t *d_pair_count, int32_t *d_status, void *stream);
+int ysb_wbf_collect(const float *d_decoded, int batch, int64_t rows, int row_width, int num_classes, float skip_thr,
+                    int multi_label, const int64_t *pass_rows, const float *pass_weights, int num_passes,
+                    float *d_records, int32_t *d_counts, int64_t capacity, void *stream);
 
 /* Self-test of the arithmetic the parity claims rest on: the sigmoid's reciprocal is spelled out (MUFU.RCP + one FMA
  * Newton step) instead of calling __frcp_rn; this compares the two for every float in [1, +inf] on the device.

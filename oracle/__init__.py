@@ -38,5 +38,6 @@ from .decode import (  # noqa: F401
 from .pipeline import FAMILY_RULES, FamilyRules, default_hyp, evaluator_nms, ImageResult  # noqa: F401
 from .softnms import (giou, diou, ciou, linear_soft_nms, exponential_soft_nms, undo_letterbox,  # noqa: F401
                       iou_backward, pairwise_iou_backward)
-from .evalside import map_iou, compute_tp  # noqa: F401
+from . import evalside  # noqa: F401
+from .evalside import map_iou, compute_tp, weighted_fusion_bbox, do_wfb  # noqa: F401
 from .tta import tta_merge, undo_pass, TTA_SCALES, TTA_FLIPS  # noqa: F401

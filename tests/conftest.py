@@ -46,7 +46,7 @@ def golden_names(prefix=""):
     # tta_* fixtures hold three head sets and the merged tensor, c1_* fixtures are seed-only full-size cases (heads are
     # regenerated, see full_size_golden): both are asked for explicitly, golden_names("tta_") / golden_names("c1_")
     return [n for n in names if n.startswith(prefix) and not n.startswith("utils_")
-            and (prefix or not n.startswith(("tta_", "c1_")))]
+            and (prefix or not n.startswith(("tta_", "c1_", "wfb_")))]
 
 
 def full_size_golden(name):

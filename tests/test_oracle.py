@@ -256,3 +256,30 @@ def test_compute_tp_matches_reference():
         np.testing.assert_array_equal(io, g[f"tp_iou_{i}"])
         seen += int(got.sum())
     assert seen > 100
+
+
+@pytest.mark.parametrize("name", golden_names("wfb_"))
+def test_do_wfb_matches_reference(name):
+    """oracle.do_wfb == the reference evaluator's __call__ with hyp['wfb'] (its np.clip call given the missing a_max)."""
+    g = load_golden(name)
+    meta = g["meta"]
+    outs = oracle.do_wfb([g[f"p{k}_preds"] for k in range(3)], meta["wfb_weights"], meta["wfb_skip_box_threshold"],
+                         meta["wfb_iou_threshold"], meta["mutil_label"])
+    for i, o in enumerate(outs):
+        c = int(g["counts"][i])
+        assert (o is None) == (c < 0)
+        if o is not None:
+            flat = np.array([f for per_label in o for f in per_label])
+            np.testing.assert_array_equal(flat, g[f"fusion_{i}"])
+
+
+def test_weighted_fusion_bbox_matches_reference():
+    g = load_golden("utils_extra")
+    for t in "abc":
+        cluster, fusion = oracle.weighted_fusion_bbox(g[f"wfb_{t}_in"], float(g[f"wfb_{t}_thr"]))
+        np.testing.assert_array_equal(np.array([f for pl in fusion for f in pl]), g[f"wfb_{t}_fusion"])
+        assert [len(pl) for pl in fusion] == g[f"wfb_{t}_labels"].tolist()
+        assert [len(c) for pl in cluster for c in pl] == g[f"wfb_{t}_sizes"].tolist()
+        np.testing.assert_array_equal(np.array([m for pl in cluster for c in pl for m in c]), g[f"wfb_{t}_members"])
+    with pytest.raises(IndexError):
+        oracle.weighted_fusion_bbox(g["wfb_degenerate_in"], 0.3)

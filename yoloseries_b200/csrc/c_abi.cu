@@ -36,6 +36,13 @@ void debug_set_nms_threads(int t);
 
 cudaError_t launch_elementwise_iou_backward(const float *b1, int64_t n1, const float *b2, int64_t n2, int kind,
                                             const float *grad_out, float *g1, float *g2, cudaStream_t stream);
+size_t wbf_workspace_bytes(int batch, int64_t stride);
+cudaError_t launch_wbf(const float *rows, int row_w, const int32_t *counts, int batch, int64_t stride, double thr, void *ws,
+                       int32_t *order, double *fusion, int32_t *members, int32_t *pairs, long long pair_cap,
+                       unsigned long long *pair_count, int32_t *status, cudaStream_t stream);
+cudaError_t launch_wbf_collect(const float *decoded, int batch, int64_t rows, int row_w, int C, float thr, int multi,
+                               const int64_t *pass_rows, const float *pass_weights, int n_pass, float *rec, int32_t *counts,
+                               int64_t cap, cudaStream_t stream);
 cudaError_t launch_selftest_reciprocal(unsigned long long *d_mismatches, cudaStream_t stream);
 cudaError_t launch_map_iou(const void *b1, int64_t n, int w1, const void *b2, int64_t m, int w2, int f64, void *out,
                            cudaStream_t stream);
@@ -614,6 +621,50 @@ int ysb_pairwise_iou_backward(const float *d_b1, int64_t n, const float *d_b2, i
     if (n > 0x7fffffffll) return YSB_ERR_LIMIT;
     return cuda_status(launch_pairwise_iou_backward(d_b1, n, d_b2, m, d_grad_out, d_grad_b1, d_grad_b2,
                                                     static_cast<cudaStream_t>(stream)));
+}
+
+int ysb_wbf_workspace_bytes(int batch, int64_t stride, size_t *bytes_out)
+{
+    if (batch < 0 || stride < 0 || !bytes_out) return YSB_ERR_BAD_ARG;
+    *bytes_out = wbf_workspace_bytes(batch, stride);
+    return YSB_OK;
+}
+
+int ysb_wbf(const float *d_rows, int row_width, const int32_t *d_counts, int batch, int64_t stride, double iou_thr,
+            void *d_workspace, size_t workspace_bytes, int32_t *d_order, double *d_fusion, int32_t *d_members,
+            int32_t *d_pairs, int64_t pair_capacity, uint64_t *d_pair_count, int32_t *d_status, void *stream)
+{
+    if (batch < 0 || stride < 0 || (row_width != 7 && row_width != 8)) return YSB_ERR_BAD_ARG;
+    if (batch == 0 || stride == 0) return YSB_OK;
+    if (!d_rows || !d_counts || !d_workspace || !d_order || !d_fusion || !d_members || !d_status) return YSB_ERR_BAD_ARG;
+    if ((d_pairs != nullptr) != (d_pair_count != nullptr) || pair_capacity < 0) return YSB_ERR_BAD_ARG;
+    if (!(iou_thr == iou_thr)) return YSB_ERR_BAD_ARG;
+    if (stride > 0x7fffffffll / 32 || batch > 65535 || static_cast<int64_t>(batch) * stride > 0x7fffffffll)
+        return YSB_ERR_LIMIT;
+    if (workspace_bytes < wbf_workspace_bytes(batch, stride)) return YSB_ERR_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(d_workspace) & 15u) return YSB_ERR_BAD_ARG;
+    return cuda_status(launch_wbf(d_rows, row_width, d_counts, batch, stride, iou_thr, d_workspace, d_order, d_fusion,
+                                  d_members, d_pairs, pair_capacity, reinterpret_cast<unsigned long long *>(d_pair_count),
+                                  d_status, static_cast<cudaStream_t>(stream)));
+}
+
+int ysb_wbf_collect(const float *d_decoded, int batch, int64_t rows, int row_width, int num_classes, float skip_thr,
+                    int multi_label, const int64_t *pass_rows, const float *pass_weights, int num_passes,
+                    float *d_records, int32_t *d_counts, int64_t capacity, void *stream)
+{
+    if (batch < 0 || rows < 0 || num_classes < 1 || row_width != 5 + num_classes) return YSB_ERR_BAD_ARG;
+    if (num_passes < 1 || num_passes > YSB_MAX_PASSES || !pass_rows || !pass_weights || !d_counts) return YSB_ERR_BAD_ARG;
+    int64_t total = 0;
+    for (int q = 0; q < num_passes; ++q) {
+        if (pass_rows[q] < 0) return YSB_ERR_BAD_ARG;
+        total += pass_rows[q];
+    }
+    if (total != rows) return YSB_ERR_BAD_ARG;
+    if (batch > 0 && rows > 0 && (!d_decoded || !d_records || capacity < 1)) return YSB_ERR_BAD_ARG;
+    if (batch > 65535 || rows * (multi_label ? num_classes : 1) > 0xffffffffll) return YSB_ERR_LIMIT;
+    return cuda_status(launch_wbf_collect(d_decoded, batch, rows, row_width, num_classes, skip_thr, multi_label != 0,
+                                          pass_rows, pass_weights, num_passes, d_records, d_counts, capacity,
+                                          static_cast<cudaStream_t>(stream)));
 }
 
 int ysb_selftest_reciprocal(uint64_t *d_mismatches, void *stream)

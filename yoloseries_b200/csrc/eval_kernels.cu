@@ -132,4 +132,271 @@ cudaError_t launch_compute_tp(const void *gt, const int64_t *gt_off, const void 
     return cudaGetLastError();
 }
 
+// ---- weighted-box-fusion, utils/weighted_fusion_bbox.py:41-96 -----------------------------------------------------------
+// Rows are (x1, y1, x2, y2, score, label, weight[, order]) float32; image i owns rows [i*stride, i*stride + counts[i]).
+// The reference walks every label's boxes in descending score order; a box joins EVERY cluster whose current fused box
+// it overlaps by IoU >= thr (cpu_iou, utils/bbox_tools.py:63-84: float32 area of the box, float64 everything else,
+// union clipped at 1e-6), or founds a new cluster; after every box all fused boxes are recomputed
+// (update_fusion_bbox :41-60: mean over members of box*score/sum(score) -- the score-weighted mean divided by the member
+// count once more -- and sum(score*weight)/sum(weight)).  Here: (1) a rank sort orders every image by (label asc, score
+// desc, later row first: argsort()[::-1] of a stable sort), (2) one warp per (image, label) segment walks it, lanes
+// strided over the clusters, cluster sums kept incrementally in float64.
+struct WbfCluster {
+    double a[4];     // sum box * score
+    double s;        // sum score
+    double sw;       // sum score * weight
+    double w;        // sum weight
+    double fus[4];   // current fused box
+    int cnt;
+    int pad;
+};
+
+__device__ __forceinline__ uint32_t sortable_f32(float v)
+{
+    const uint32_t b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(256) k_wbf_keys(const float *__restrict__ rows, int row_w, const int32_t *__restrict__ counts,
+                                                  int64_t stride, uint64_t *__restrict__ k1, uint32_t *__restrict__ k2)
+{
+    const int img = blockIdx.y;
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j >= counts[img]) return;
+    const float *r = rows + (static_cast<int64_t>(img) * stride + j) * row_w;
+    const int label = static_cast<int>(r[5]);
+    k1[img * stride + j] = (static_cast<uint64_t>(static_cast<uint32_t>(0x7fffffff - label)) << 32) | sortable_f32(r[4]);
+    k2[img * stride + j] = row_w >= 8 ? __float_as_uint(r[7]) : static_cast<uint32_t>(j);
+}
+
+// rank = number of rows of the image that sort before this one (descending (k1, k2)); keys are distinct per image.
+__global__ void __launch_bounds__(256) k_wbf_rank(const int32_t *__restrict__ counts, int64_t stride,
+                                                  const uint64_t *__restrict__ k1, const uint32_t *__restrict__ k2,
+                                                  int32_t *__restrict__ order, uint64_t *__restrict__ sorted_k1)
+{
+    const int img = blockIdx.y;
+    const int n = counts[img];
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint64_t *a1 = k1 + img * stride;
+    const uint32_t *a2 = k2 + img * stride;
+    const uint64_t m1 = a1[j];
+    const uint32_t m2 = a2[j];
+    int rank = 0;
+    for (int i = 0; i < n; ++i) {
+        const uint64_t o1 = __ldg(a1 + i);
+        rank += (o1 > m1 || (o1 == m1 && __ldg(a2 + i) > m2)) ? 1 : 0;
+    }
+    order[img * stride + rank] = static_cast<int32_t>(j);
+    sorted_k1[img * stride + rank] = m1;
+}
+
+// cpu_iou(box (float32), fused (float64)), utils/bbox_tools.py:63-84
+__device__ __forceinline__ double wbf_iou(const float *b, const double *f)
+{
+    const double a1 = static_cast<double>(__fmul_rn(__fsub_rn(b[2], b[0]), __fsub_rn(b[3], b[1])));  // np.prod of float32 sides
+    const double a2 = (f[2] - f[0]) * (f[3] - f[1]);
+    const double bx1 = b[0], by1 = b[1], bx2 = b[2], by2 = b[3];
+    const double ymax = by2 < f[3] ? by2 : f[3], xmax = bx2 < f[2] ? bx2 : f[2];
+    const double ymin = by1 > f[1] ? by1 : f[1], xmin = bx1 > f[0] ? bx1 : f[0];
+    double w = xmax - xmin, h = ymax - ymin;
+    w = w > 0.0 ? w : 0.0;
+    h = h > 0.0 ? h : 0.0;
+    const double inter = w * h;
+    double den = a1 + a2 - inter;
+    den = den < 1e-6 ? 1e-6 : den;
+    return inter / den;
+}
+
+// One warp per sorted position; only the warps that sit on the first row of a label segment work.
+__global__ void __launch_bounds__(256) k_wbf_cluster(const float *__restrict__ rows, int row_w, const int32_t *__restrict__ counts,
+                                                     int64_t stride, double thr, const int32_t *__restrict__ order,
+                                                     const uint64_t *__restrict__ sorted_k1, WbfCluster *__restrict__ clusters,
+                                                     double *__restrict__ fusion, int32_t *__restrict__ members,
+                                                     int32_t *__restrict__ pairs, long long pair_cap,
+                                                     unsigned long long *__restrict__ pair_count, int32_t *__restrict__ status)
+{
+    const int img = blockIdx.y;
+    const int n = counts[img];
+    const int64_t p0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (p0 >= n) return;
+    const int64_t base = static_cast<int64_t>(img) * stride;
+    const uint32_t lab_key = static_cast<uint32_t>(sorted_k1[base + p0] >> 32);
+    if (p0 > 0 && static_cast<uint32_t>(sorted_k1[base + p0 - 1] >> 32) == lab_key) return;   // not a segment start
+    int64_t p1 = p0 + 1;
+    while (p1 < n && static_cast<uint32_t>(sorted_k1[base + p1] >> 32) == lab_key) ++p1;
+    WbfCluster *cl = clusters + base + p0;
+    // fusion_bbox = [top box], cluster_bbox = [[]] (:73-74)
+    const float *top = rows + (base + order[base + p0]) * row_w;
+    if (lane == 0) {
+        WbfCluster c{};
+        for (int q = 0; q < 4; ++q) c.fus[q] = static_cast<double>(top[q]);
+        cl[0] = c;
+    }
+    __syncwarp();
+    int nclus = 1;
+    bool broken = false;
+    for (int64_t k = p0; k < p1; ++k) {
+        const float *r = rows + (base + order[base + k]) * row_w;
+        const double sc = static_cast<double>(r[4]), wt = static_cast<double>(r[6]);
+        bool hit_any = false;
+        for (int c = lane; c < nclus; c += 32) {
+            WbfCluster &C = cl[c];
+            if (wbf_iou(r, C.fus) >= thr) {
+                hit_any = true;
+                for (int q = 0; q < 4; ++q) C.a[q] += static_cast<double>(r[q]) * sc;
+                C.s += sc;
+                C.sw += sc * wt;
+                C.w += wt;
+                C.cnt += 1;
+                for (int q = 0; q < 4; ++q) C.fus[q] = C.a[q] / C.s / static_cast<double>(C.cnt);
+                if (pairs) {
+                    const unsigned long long at = atomicAdd(pair_count, 1ull);
+                    if (at < static_cast<unsigned long long>(pair_cap)) {
+                        pairs[2 * at] = static_cast<int32_t>(base + p0 + c);   // global slot / position indices
+                        pairs[2 * at + 1] = static_cast<int32_t>(base + k);
+                    }
+                }
+            }
+        }
+        hit_any = __any_sync(0xffffffffu, hit_any);
+        if (!hit_any) {
+            if (k == p0) { broken = true; break; }   // the top box misses itself: cluster 0 stays empty, the reference raises
+            if (lane == 0) {
+                WbfCluster c{};
+                for (int q = 0; q < 4; ++q) { c.a[q] = static_cast<double>(r[q]) * sc; }
+                c.s = sc;
+                c.sw = sc * wt;
+                c.w = wt;
+                c.cnt = 1;
+                for (int q = 0; q < 4; ++q) c.fus[q] = c.a[q] / c.s / 1.0;
+                cl[nclus] = c;
+                if (pairs) {
+                    const unsigned long long at = atomicAdd(pair_count, 1ull);
+                    if (at < static_cast<unsigned long long>(pair_cap)) {
+                        pairs[2 * at] = static_cast<int32_t>(base + p0 + nclus);
+                        pairs[2 * at + 1] = static_cast<int32_t>(base + k);
+                    }
+                }
+            }
+            ++nclus;
+        }
+        __syncwarp();
+    }
+    if (broken) {
+        if (lane == 0) atomicExch(status + img, 1);
+        return;
+    }
+    const double label = static_cast<double>(top[5]);
+    for (int c = lane; c < nclus; c += 32) {
+        const WbfCluster &C = cl[c];
+        double *f = fusion + (base + p0 + c) * 6;
+        for (int q = 0; q < 4; ++q) f[q] = C.fus[q];
+        f[4] = C.sw / C.w;
+        f[5] = label;
+        members[base + p0 + c] = C.cnt;
+    }
+}
+
+// do_wfb's per-pass filter (trainer/eval_yolov5.py:57-79; v7 / YOLOX identical) on the decoded rows of all passes:
+// obj > thr, conf = cls * obj (float32), best class (first maximum) with conf > thr -- or, mutil_label, every class above
+// it --, xywh -> xyxy, the pass weight; one record per survivor appended to the image's list (order restored by the sort
+// through column 7 = position in the reference's stacked list).
+struct WbfPasses {
+    long long first_row[YSB_MAX_PASSES + 1];
+    float weight[YSB_MAX_PASSES];
+    int n;
+};
+
+__global__ void __launch_bounds__(256) k_wbf_collect(const float *__restrict__ decoded, int64_t rows, int row_w, int C,
+                                                     float thr, int multi, const __grid_constant__ WbfPasses passes,
+                                                     float *__restrict__ rec, int32_t *__restrict__ counts, int64_t cap)
+{
+    const int img = blockIdx.y;
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j >= rows) return;
+    const float *r = decoded + (static_cast<int64_t>(img) * rows + j) * row_w;
+    const float obj = r[4];
+    if (!(obj > thr)) return;
+    float weight = passes.weight[0];
+    for (int q = 1; q < passes.n; ++q)
+        if (j >= passes.first_row[q]) weight = passes.weight[q];
+    const float hw = __fmul_rn(r[2], 0.5f), hh = __fmul_rn(r[3], 0.5f);   // w / 2 is exact either way
+    const float x1 = __fsub_rn(r[0], hw), y1 = __fsub_rn(r[1], hh), x2 = __fadd_rn(r[0], hw), y2 = __fadd_rn(r[1], hh);
+    auto emit = [&](float conf, int cls, uint32_t pos) {
+        const int at = atomicAdd(counts + img, 1);
+        if (at >= cap) return;
+        float *o = rec + (static_cast<int64_t>(img) * cap + at) * 8;
+        o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2;
+        o[4] = conf;
+        o[5] = static_cast<float>(cls);
+        o[6] = weight;
+        o[7] = __uint_as_float(pos);
+    };
+    if (multi) {
+        for (int k = 0; k < C; ++k) {
+            const float conf = __fmul_rn(r[5 + k], obj);
+            if (conf > thr) emit(conf, k, static_cast<uint32_t>(j) * static_cast<uint32_t>(C) + static_cast<uint32_t>(k));
+        }
+    } else {
+        float best = __fmul_rn(r[5], obj);
+        int bk = 0;
+        for (int k = 1; k < C; ++k) {
+            const float conf = __fmul_rn(r[5 + k], obj);
+            if (conf > best) { best = conf; bk = k; }
+        }
+        if (best > thr) emit(best, bk, static_cast<uint32_t>(j));
+    }
+}
+
+size_t wbf_workspace_bytes(int batch, int64_t stride)
+{
+    const size_t slots = static_cast<size_t>(batch) * static_cast<size_t>(stride);
+    return slots * (sizeof(WbfCluster) + 2 * sizeof(uint64_t) + sizeof(uint32_t)) + 64;
+}
+
+cudaError_t launch_wbf(const float *rows, int row_w, const int32_t *counts, int batch, int64_t stride, double thr, void *ws,
+                       int32_t *order, double *fusion, int32_t *members, int32_t *pairs, long long pair_cap,
+                       unsigned long long *pair_count, int32_t *status, cudaStream_t stream)
+{
+    if (batch == 0 || stride == 0) return cudaSuccess;
+    const size_t slots = static_cast<size_t>(batch) * static_cast<size_t>(stride);
+    WbfCluster *clusters = static_cast<WbfCluster *>(ws);
+    uint64_t *k1 = reinterpret_cast<uint64_t *>(clusters + slots);
+    uint64_t *sk1 = k1 + slots;
+    uint32_t *k2 = reinterpret_cast<uint32_t *>(sk1 + slots);
+    cudaError_t e = cudaMemsetAsync(status, 0, sizeof(int32_t) * batch, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(members, 0, sizeof(int32_t) * slots, stream);
+    if (e == cudaSuccess && pair_count) e = cudaMemsetAsync(pair_count, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
+    const dim3 g1(static_cast<unsigned>((stride + 255) / 256), static_cast<unsigned>(batch));
+    k_wbf_keys<<<g1, 256, 0, stream>>>(rows, row_w, counts, stride, k1, k2);
+    k_wbf_rank<<<g1, 256, 0, stream>>>(counts, stride, k1, k2, order, sk1);
+    const dim3 g2(static_cast<unsigned>((stride * 32 + 255) / 256), static_cast<unsigned>(batch));
+    k_wbf_cluster<<<g2, 256, 0, stream>>>(rows, row_w, counts, stride, thr, order, sk1, clusters, fusion, members, pairs,
+                                          pair_cap, pair_count, status);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_wbf_collect(const float *decoded, int batch, int64_t rows, int row_w, int C, float thr, int multi,
+                               const int64_t *pass_rows, const float *pass_weights, int n_pass, float *rec, int32_t *counts,
+                               int64_t cap, cudaStream_t stream)
+{
+    cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int32_t) * (batch > 0 ? batch : 1), stream);
+    if (e != cudaSuccess || batch == 0 || rows == 0) return e;
+    WbfPasses P{};
+    P.n = n_pass;
+    long long at = 0;
+    for (int q = 0; q < n_pass; ++q) {
+        P.first_row[q] = at;
+        P.weight[q] = pass_weights[q];
+        at += pass_rows[q];
+    }
+    P.first_row[n_pass] = at;
+    const dim3 grid(static_cast<unsigned>((rows + 255) / 256), static_cast<unsigned>(batch));
+    k_wbf_collect<<<grid, 256, 0, stream>>>(decoded, rows, row_w, C, thr, multi, P, rec, counts, cap);
+    return cudaGetLastError();
+}
+
 }  // namespace ysb

@@ -48,7 +48,8 @@ class _Evaluator:
         original-picture pixels."""
         if self.use_tta:
             if self.hyp.get("wfb", False):
-                raise NotImplementedError("weighted-box-fusion (hyp['wfb']) is a 'next' row (SURVEY.md 8f rank 3)")
+                _, independent = self.test_time_augmentation(inputs)
+                return self.do_wfb(independent)
             # three model forwards, then ONE fused call: no decoded or merged tensor is written (ysb_postprocess_tta)
             out = self._pp.run_tta(self._tta_passes(inputs), (inputs.size(2), inputs.size(3)), info=info)
             return self._pp.to_list(out)
@@ -73,6 +74,53 @@ class _Evaluator:
         h, w = self.hyp["input_img_size"]
         out = self._pp.run(preds, int(h), int(w), decoded=True)
         return self._pp.to_list(out, as_numpy=True)
+
+    def do_wfb(self, preds_out):
+        """trainer/eval_yolov5.py:44-92 (the same method in eval_yolov7.py / eval_yolox.py): weighted-box-fusion of the
+        per-pass decoded tensors [(b, X, 5+C), (b, Y, 5+C), ...] -> list over images of the reference's nesting
+        ``[[fused (6,) float64 arrays of label 0], [... label 1], ...]`` or None for an image without survivors.
+        Filter (ysb_wbf_collect) and fusion (ysb_wbf) run on the device for the whole batch at once.
+
+        RetinaNet / FCOS: the reference's do_wfb indexes ``[cls..., box]`` columns its own do_inference does not produce
+        and appends None inside the pass loop (eval_fcos.py:40-90, eval_retinanet.py:77-130) -- not mirrored."""
+        import ctypes
+
+        from .. import _lib
+        from ..utils.weighted_fusion_bbox import fuse_batch
+        if self.family not in ("yolov5", "yolov7", "yolox"):
+            raise NotImplementedError(f"do_wfb of {self.family}: the reference's own method does not match its decode layout")
+        weights = self.hyp.get("wfb_weights", [1.0 for _ in range(len(preds_out))])
+        preds = [p.detach().to(torch.float32) for p in preds_out]
+        preds = [p if p.device.type == "cuda" else p.cuda() for p in preds]
+        dev = preds[0].device
+        merged = preds[0].contiguous() if len(preds) == 1 else torch.cat(preds, dim=1).contiguous()
+        batch, rows, row_w = merged.shape
+        C = int(self.num_class)
+        multi = bool(self.hyp["mutil_label"])
+        cap = rows * (C if multi else 1)
+        rec = torch.empty((batch, max(cap, 1), 8), dtype=torch.float32, device=dev)
+        counts = torch.empty((max(batch, 1),), dtype=torch.int32, device=dev)
+        n = len(preds)
+        pass_rows = (ctypes.c_int64 * n)(*[int(p.shape[1]) for p in preds])
+        pass_w = (ctypes.c_float * n)(*[float(weights[i]) for i in range(n)])
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().ysb_wbf_collect(
+                merged.data_ptr(), batch, rows, row_w, C, float(self.hyp["wfb_skip_box_threshold"]), int(multi), pass_rows,
+                pass_w, n, rec.data_ptr(), counts.data_ptr(), cap,
+                ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "ysb_wbf_collect")
+            kmax = int(counts[:batch].max().item()) if batch else 0
+            if kmax == 0:
+                return [None] * batch
+            # the fusion works on the occupied part of every image's record list
+            fused = fuse_batch(rec[:, :kmax].contiguous(), counts[:batch], float(self.hyp["wfb_iou_threshold"]), 8)
+        out = []
+        for item in fused:
+            if item is None:
+                out.append(None)
+                continue
+            fus = item[0]
+            out.append([[fus[k].copy() for k in np.nonzero(fus[:, 5] == lab)[0]] for lab in np.unique(fus[:, 5])])
+        return out
 
     def do_nms(self, preds_out):
         """Dead code in the reference (no caller; raises IndexError for iou_type='iou').  Mirrored
