@@ -307,7 +307,7 @@ def run_ours(args):
         if int(os.environ.get("LOCAL_RANK", "0")) == 0:
             from yoloseries_b200 import build as ysb_build
             print("bench.py: libysb_postproc.so missing, building it with nvcc ...", file=sys.stderr)
-            ysb_build.build()
+            ysb_build.build_all()
         else:  # the other ranks wait for rank 0's build (the link is renamed into place atomically)
             deadline = time.time() + 900
             while not os.path.exists(_lib.LIB_PATH) and time.time() < deadline:

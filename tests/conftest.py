@@ -21,9 +21,11 @@ def pytest_configure(config):
 def _built_library():
     """The in-tree libysb_postproc.so normally travels with the snapshot; a fresh checkout (the .so is git-ignored)
     gets it built once per session.  Building is not a fallback: without nvcc this raises and every test fails loudly."""
-    from yoloseries_b200 import _lib, build
+    from yoloseries_b200 import _lib, _ops, build
     if not os.path.exists(_lib.LIB_PATH) and not os.environ.get("YSB_LIBRARY"):
         build.build()
+    if not os.path.exists(_ops.ADAPTER_PATH):
+        build.build_torch_adapter()
     yield
 
 

@@ -200,3 +200,32 @@ def test_tta_entry_points_validate_on_the_host(lib):
     assert lib.ysb_num_candidates(ctypes.byref(dec), ctypes.byref(n), None) == _lib.YSB_ERR_BAD_ARG
     assert lib.ysb_postprocess_tta(arr, 3, None, None, None, 0, None, None, None, None) == _lib.YSB_ERR_BAD_ARG
     assert lib.ysb_decode_into(ctypes.byref(base), None, 3, None, 25200, 0, None) == _lib.YSB_ERR_BAD_ARG
+
+
+def test_torch_extension_loads_and_registers_the_operators():
+    """csrc/torch_adapter.cpp -> _lib/libysb_torch.so: TORCH_LIBRARY(ysb) over the C ABI.  Loadable without a GPU; every
+    operator refuses CPU tensors (no fallback) with the reference's exception type, before any CUDA call."""
+    import torch
+
+    from yoloseries_b200 import _lib, _ops
+    ops = _ops.load()
+    assert ops.abi_version() == _lib.ABI_VERSION
+    assert ops.params_bytes() == ctypes.sizeof(_lib.YsbParams)
+    for name in ("postprocess", "filter_candidates", "select_nms", "decode", "decode_into", "nms", "pairwise_iou",
+                 "pairwise_iou_backward", "elementwise_iou", "elementwise_iou_backward"):
+        assert hasattr(ops, name), name
+    p = _lib.YsbParams()
+    blob = _ops.params_tensor(p)
+    p.batch = 5                                           # the tensor shares the struct's memory
+    assert blob.numel() == ctypes.sizeof(_lib.YsbParams) and int(blob[8:12].view(torch.int32)[0]) == 5
+    with pytest.raises(ValueError):
+        ops.pairwise_iou(torch.zeros(2, 4), torch.zeros(3, 4), _lib.IOU_F32)
+    with pytest.raises(ValueError):
+        ops.nms(torch.zeros(2, 4), torch.zeros(2), 0.5, _lib.CMP_GE, _lib.IOU_NUMBA_F64MIX, 0)
+    with pytest.raises(ValueError):
+        ops.decode([torch.zeros(1, 255, 8, 8)], blob)
+    with pytest.raises(ValueError):
+        ops.decode([], blob)
+    with pytest.raises(ValueError):                       # a params blob of the wrong size
+        ops.filter_candidates([torch.zeros(1)], torch.zeros(10, dtype=torch.uint8), torch.zeros(1, 1, dtype=torch.int64),
+                              torch.zeros(1, 4, dtype=torch.int32))

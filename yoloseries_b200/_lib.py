@@ -172,7 +172,8 @@ def load():
             raise ImportError(
                 f"{LIB_PATH} not found: build it with `python -m yoloseries_b200.build` "
                 "(or __graft_entry__.build()); yoloseries_b200 has no CPU/PyTorch fallback")
-        lib = ctypes.CDLL(LIB_PATH)
+        # RTLD_GLOBAL: the torch extension (libysb_torch.so, _ops.py) binds its ysb_* symbols to THIS library
+        lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype = res

@@ -73,8 +73,45 @@ def build(force=False, verbose=False, extra_flags=(), lib=LIB, tag=""):
     return lib
 
 
+ADAPTER_SRC = os.path.join(CSRC, "torch_adapter.cpp")
+ADAPTER_LIB = os.path.join(OUT_DIR, "libysb_torch.so")
+
+
+def build_torch_adapter(force=False):
+    """The thin PyTorch C++ extension over the C ABI (csrc/torch_adapter.cpp -> _lib/libysb_torch.so): host C++ only,
+    compiled with g++ against torch's headers, in-tree.  It does NOT link libysb_postproc.so: its ysb_* symbols resolve
+    against whichever build of the C-ABI library yoloseries_b200._lib loaded (RTLD_GLOBAL) before it -- the product
+    library, or a profiling build selected with YSB_LIBRARY."""
+    deps = [ADAPTER_SRC, os.path.join(ROOT, "include", "ysb_postproc.h")]
+    if not force and os.path.exists(ADAPTER_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(ADAPTER_LIB) for d in deps):
+        return ADAPTER_LIB
+    import torch
+    from torch.utils import cpp_extension as ce
+    os.makedirs(OUT_DIR, exist_ok=True)
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    tmp = ADAPTER_LIB + f".tmp{os.getpid()}"
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas",
+           f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}", "-I", os.path.join(ROOT, "include"),
+           *[a for p in ce.include_paths() for a in ("-isystem", p)], "-isystem", os.path.join(cuda_home, "include"),
+           ADAPTER_SRC, "-o", tmp,
+           *[a for p in ce.library_paths() for a in ("-L" + p, "-Wl,-rpath," + p)],
+           "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"g++ failed for torch_adapter.cpp:\n{r.stdout}\n{r.stderr[-4000:]}")
+    os.replace(tmp, ADAPTER_LIB)
+    return ADAPTER_LIB
+
+
+def build_all(force=False):
+    lib = build(force=force)
+    build_torch_adapter(force=force)
+    return lib
+
+
 if __name__ == "__main__":
     if "--variants" in sys.argv:
         print(build_variants(verbose="-v" in sys.argv))
     else:
         print(build(force=True, verbose="-v" in sys.argv, extra_flags=[a for a in sys.argv[1:] if a.startswith("-D")]))
+        print(build_torch_adapter(force=True))

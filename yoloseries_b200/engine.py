@@ -9,7 +9,7 @@ from collections import OrderedDict
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, _ops
 from ._lib import YsbParams
 
 # strides fixed by the reference evaluators (self.ds_scales), trainer/eval_yolov5.py:21, eval_yolov7.py, eval_fcos.py:18
@@ -290,6 +290,7 @@ class PostProcessor:
         self.anchors = anchors
         self.compute_metric = compute_metric
         self._lib = _lib.load()
+        self._ops = _ops.load()
         self._cache = {}
 
     # ---- plumbing ------------------------------------------------------------------------------------------
@@ -323,7 +324,7 @@ class PostProcessor:
             ws = ctypes.c_size_t()
             _lib.check(self._lib.ysb_postprocess_workspace_bytes(ctypes.byref(params), ctypes.byref(ws)),
                        "ysb_postprocess_workspace_bytes")
-            ent = dict(params=params, N=n.value, row_w=rw.value,
+            ent = dict(params=params, params_t=_ops.params_tensor(params), N=n.value, row_w=rw.value,
                        workspace=torch.empty(max(ws.value, 1), dtype=torch.uint8, device=dev),
                        out=DetectionBuffers(batch, params.max_det, dev))
             self._cache[key] = ent
@@ -344,13 +345,7 @@ class PostProcessor:
         flat = flatten_heads(self.family, heads)
         batch = flat[0].shape[0]
         ent = self._prepare(flat, batch, img_h, img_w, _lib.INPUT_RAW_HEADS)
-        out = torch.empty((batch, ent["N"], ent["row_w"]), dtype=torch.float32, device=flat[0].device)
-        ptrs = _lib.head_pointer_array(flat)
-        dev = flat[0].device
-        with torch.cuda.device(dev):
-            _lib.check(self._lib.ysb_decode(ctypes.byref(ent["params"]), ptrs, len(flat), out.data_ptr(),
-                                            self._stream(dev)), "ysb_decode")
-        return out
+        return self._ops.decode(flat, ent["params_t"])
 
     def _letterbox(self, holder, params_list, info, batch, dev):
         """Stage the reference's per-image info dicts as the (b, 5) table the NMS kernel's row write reads (fused
@@ -376,14 +371,12 @@ class PostProcessor:
         kind = _lib.INPUT_DECODED_ROWS if decoded else _lib.INPUT_RAW_HEADS
         ent = self._prepare(flat, batch, img_h, img_w, kind)
         out = ent["out"]
-        ptrs = _lib.head_pointer_array(flat)
         ws = ent["workspace"]
         dev = flat[0].device
-        with torch.cuda.device(dev):   # kernels, function attributes and the stream all belong to the heads' device
+        with torch.cuda.device(dev):
             self._letterbox(ent, [ent["params"]], info, batch, dev)
-            _lib.check(self._lib.ysb_postprocess(ctypes.byref(ent["params"]), ptrs, len(flat), ws.data_ptr(), ws.numel(),
-                                                 out.dets.data_ptr(), out.det_idx.data_ptr(), out.det_cnt.data_ptr(),
-                                                 self._stream(dev)), "ysb_postprocess")
+        # through the torch extension (csrc/torch_adapter.cpp): tensor checks, device guard, torch's current stream
+        self._ops.postprocess(flat, ent["params_t"], ws, out.dets, out.det_idx, out.det_cnt)
         return out
 
     # ---- test-time augmentation (trainer/eval_yolov5.py:152-179 and the same method of every evaluator) ------------
@@ -409,9 +402,7 @@ class PostProcessor:
         off, views = 0, []
         dev = out.device
         for flat, ent in ents:
-            with torch.cuda.device(dev):
-                _lib.check(self._lib.ysb_decode_into(ctypes.byref(ent["params"]), _lib.head_pointer_array(flat), len(flat),
-                                                     out.data_ptr(), total, off, self._stream(dev)), "ysb_decode_into")
+            self._ops.decode_into(flat, ent["params_t"], out, off)
             views.append(out[:, off:off + ent["N"]])
             off += ent["N"]
         return out, views
@@ -478,11 +469,7 @@ class PostProcessor:
         slots = ent["N"] * (int(self.hyp["num_class"]) if self.hyp["mutil_label"] else 1)
         keys = torch.empty((batch, slots), dtype=torch.int64, device=dev)
         counts = torch.empty((batch, 4), dtype=torch.int32, device=dev)
-        ptrs = _lib.head_pointer_array(flat)
-        with torch.cuda.device(dev):
-            _lib.check(self._lib.ysb_filter_candidates(ctypes.byref(ent["params"]), ptrs, len(flat), keys.data_ptr(),
-                                                       slots, counts.data_ptr(), self._stream(dev)),
-                       "ysb_filter_candidates")
+        self._ops.filter_candidates(flat, ent["params_t"], keys, counts)
         return keys, counts
 
     def undo_letterbox(self, out, info):

@@ -4,7 +4,7 @@ import ctypes
 import numpy as np
 import torch
 
-from .. import _lib
+from .. import _lib, _ops
 
 
 def cuda_device():
@@ -31,19 +31,7 @@ def to_cuda_f32(x, device=None):
 
 
 def nms_indices(boxes, scores, iou_threshold, iou_kind, cmp, max_keep=0):
-    """ysb_nms on CUDA tensors -> python list of kept indices (visiting order)."""
-    lib = _lib.load()
-    m = boxes.shape[0]
-    ws_bytes = ctypes.c_size_t()
-    _lib.check(lib.ysb_nms_workspace_bytes(m, ctypes.byref(ws_bytes)), "ysb_nms_workspace_bytes")
-    dev = boxes.device
-    ws = torch.empty(max(ws_bytes.value, 1), dtype=torch.uint8, device=dev)
-    cap = m if max_keep <= 0 else min(m, max_keep)
-    keep = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
-    cnt = torch.zeros(1, dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
-        _lib.check(lib.ysb_nms(boxes.data_ptr(), scores.data_ptr(), m, float(iou_threshold), cmp, iou_kind,
-                               int(max_keep), ws.data_ptr(), ws.numel(), keep.data_ptr(), cnt.data_ptr(),
-                               stream_ptr()), "ysb_nms")
-    n = int(cnt.item())
-    return keep[:n].cpu().tolist()
+    """torch.ops.ysb.nms (ysb_nms behind the torch extension) on CUDA tensors -> python list of kept indices (visiting
+    order).  Workspace and outputs come from torch's caching allocator inside the operator."""
+    keep, cnt = _ops.load().nms(boxes, scores, float(iou_threshold), int(cmp), int(iou_kind), int(max_keep))
+    return keep[: int(cnt.item())].cpu().tolist()

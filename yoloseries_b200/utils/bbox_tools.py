@@ -1,4 +1,5 @@
-"""Drop-in mirrors of the IoU routines of utils/bbox_tools.py; compute runs in libysb_postproc.so.
+"""Drop-in mirrors of the IoU routines of utils/bbox_tools.py: torch.ops.ysb.* (the thin torch extension,
+csrc/torch_adapter.cpp) over the C ABI of libysb_postproc.so.
 
 The row-wise GIoU / DIoU / CIoU are differentiable (torch.autograd.Function over ysb_elementwise_iou /
 ysb_elementwise_iou_backward) because the reference's losses differentiate through them (loss/yolov5_loss.py:110,
@@ -9,7 +10,7 @@ decorator), so the result must carry a grad_fn exactly like the reference's torc
 import numpy as np
 import torch
 
-from .. import _lib
+from .. import _lib, _ops
 from ._common import stream_ptr, to_cuda_f32
 
 __all__ = ["numba_iou", "gpu_iou", "gpu_Giou", "gpu_DIoU", "gpu_CIoU"]
@@ -19,19 +20,11 @@ def numba_iou(bbox1, bbox2):
     """utils/bbox_tools.py:12-35 -- (M,4) f32, (N,4) f32 ndarrays -> (M,N) float64 ndarray (no clamp, NaN for 0/0)."""
     b1 = to_cuda_f32(np.asarray(bbox1).reshape(-1, 4))
     b2 = to_cuda_f32(np.asarray(bbox2).reshape(-1, 4), b1.device)
-    out = torch.empty((b1.shape[0], b2.shape[0]), dtype=torch.float64, device=b1.device)
-    with torch.cuda.device(b1.device):
-        _lib.check(_lib.load().ysb_pairwise_iou(b1.data_ptr(), b1.shape[0], b2.data_ptr(), b2.shape[0],
-                                                _lib.IOU_NUMBA_F64MIX, out.data_ptr(), stream_ptr()), "ysb_pairwise_iou")
-    return out.cpu().numpy()
+    return _ops.load().pairwise_iou(b1, b2, _lib.IOU_NUMBA_F64MIX).cpu().numpy()
 
 
 def _pairwise_forward(b1, b2):
-    out = torch.empty((b1.shape[0], b2.shape[0]), dtype=torch.float32, device=b1.device)
-    with torch.cuda.device(b1.device):
-        _lib.check(_lib.load().ysb_pairwise_iou(b1.data_ptr(), b1.shape[0], b2.data_ptr(), b2.shape[0], _lib.IOU_F32,
-                                                out.data_ptr(), stream_ptr()), "ysb_pairwise_iou")
-    return out
+    return _ops.load().pairwise_iou(b1, b2, _lib.IOU_F32)
 
 
 class _PairwiseIoU(torch.autograd.Function):
@@ -52,13 +45,7 @@ class _PairwiseIoU(torch.autograd.Function):
         shape1, dtype1, dev1, shape2, dtype2, dev2 = ctx.meta
         need1, need2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         g = to_cuda_f32(grad_out.reshape(b1.shape[0], b2.shape[0]), b1.device)
-        g1 = torch.empty_like(b1) if need1 else None
-        g2 = torch.empty_like(b2) if need2 else None
-        with torch.cuda.device(b1.device):
-            _lib.check(_lib.load().ysb_pairwise_iou_backward(
-                b1.data_ptr(), b1.shape[0], b2.data_ptr(), b2.shape[0], g.data_ptr(),
-                g1.data_ptr() if need1 else None, g2.data_ptr() if need2 else None, stream_ptr()),
-                "ysb_pairwise_iou_backward")
+        g1, g2 = _ops.load().pairwise_iou_backward(b1, b2, g, need1, need2)
         if need1:
             g1 = g1.reshape(shape1).to(device=dev1, dtype=dtype1)
         if need2:
@@ -76,11 +63,7 @@ def gpu_iou(bbox1, bbox2):
 
 
 def _rowwise_forward(kind, b1, b2):
-    out = torch.empty((b2.shape[0],), dtype=torch.float32, device=b2.device)
-    with torch.cuda.device(b2.device):
-        _lib.check(_lib.load().ysb_elementwise_iou(b1.data_ptr(), b1.shape[0], b2.data_ptr(), b2.shape[0], kind,
-                                                   out.data_ptr(), stream_ptr()), "ysb_elementwise_iou")
-    return out
+    return _ops.load().elementwise_iou(b1, b2, kind)
 
 
 class _RowwiseIoU(torch.autograd.Function):
@@ -102,13 +85,7 @@ class _RowwiseIoU(torch.autograd.Function):
         shape1, dtype1, dev1, shape2, dtype2, dev2 = ctx.meta
         need1, need2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         g = to_cuda_f32(grad_out.reshape(-1), b2.device)
-        g1 = torch.empty_like(b1) if need1 else None
-        g2 = torch.empty_like(b2) if need2 else None
-        with torch.cuda.device(b2.device):
-            _lib.check(_lib.load().ysb_elementwise_iou_backward(
-                b1.data_ptr(), b1.shape[0], b2.data_ptr(), b2.shape[0], ctx.kind, g.data_ptr(),
-                g1.data_ptr() if need1 else None, g2.data_ptr() if need2 else None, stream_ptr()),
-                "ysb_elementwise_iou_backward")
+        g1, g2 = _ops.load().elementwise_iou_backward(b1, b2, ctx.kind, g, need1, need2)
         if need1:
             g1 = g1.reshape(shape1).to(device=dev1, dtype=dtype1)
         if need2:
