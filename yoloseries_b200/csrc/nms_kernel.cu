@@ -844,6 +844,11 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
         lb_hi_y = __fsub_rn(__ldg(t + 3), 1.0f);
         lb_hi_x = __fsub_rn(__ldg(t + 4), 1.0f);
     }
+    // Rows are first laid out in shared memory (the tranche's box array is free by now), then copied out with full-width
+    // contiguous stores -- to the caller's buffer or, in a detection gather, to every rank's receive slot.  (Storing the
+    // six floats of a row one by one cost 6 partial-sector writes per row and destination: over NVLink, with 8
+    // destinations, that tripled the kernel's time.)
+    float *stage = reinterpret_cast<float *>(S.raw);   // kTranche * 16 B >= max_det (<= 1024) * 24 B
     int written = 0;
     for (int r0 = 0; r0 < kept; r0 += THREADS) {
         const int r = r0 + tid;
@@ -878,19 +883,33 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
                 box.y = fminf(fmaxf(__fdiv_rn(__fsub_rn(box.y, lb_top), lb_scale), 1.0f), lb_hi_y);
                 box.w = fminf(fmaxf(__fdiv_rn(__fsub_rn(box.w, lb_top), lb_scale), 1.0f), lb_hi_y);
             }
-            const size_t off = (static_cast<size_t>(img) * max_det + at) * 6;
-            // one destination (the caller's buffer) or, in a detection gather, every rank's receive slot: plain stores,
-            // local or over NVLink; a warp writes 32 consecutive rows = 768 contiguous bytes
-            const int ndst = G.world > 0 ? G.world : 1;
-            for (int d = 0; d < ndst; ++d) {
-                float *row = (G.world > 0 ? G.rows[d] : dets) + off;
-                row[0] = box.x; row[1] = box.y; row[2] = box.z; row[3] = box.w;
-                row[4] = s_out;
-                row[5] = c_out;
-            }
+            float *row = stage + at * 6;
+            row[0] = box.x; row[1] = box.y; row[2] = box.z; row[3] = box.w;
+            row[4] = s_out;
+            row[5] = c_out;
             if (det_idx) det_idx[static_cast<size_t>(img) * max_det + at] = static_cast<int32_t>(key_cand(key));
         }
         written = total;
+    }
+    {
+        const int nfl = written * 6;
+        const int nfl4 = (nfl + 3) & ~3;
+        if (tid < nfl4 - nfl) stage[nfl + tid] = 0.0f;   // the last 16-byte store may reach past the rows: defined bytes
+        __syncthreads();
+        const size_t img_off = static_cast<size_t>(img) * max_det * 6;
+        const int ndst = G.world > 0 ? G.world : 1;
+        // a 16-byte store needs an even max_det (image rows start on 16-byte boundaries) and must stay inside the image
+        const bool wide = (max_det & 1) == 0;
+        for (int d = 0; d < ndst; ++d) {
+            float *dst = (G.world > 0 ? G.rows[d] : dets) + img_off;
+            if (wide && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+                for (int e = tid; e < nfl4 / 4; e += THREADS)
+                    reinterpret_cast<float4 *>(dst)[e] = reinterpret_cast<const float4 *>(stage)[e];
+            } else {
+                for (int e = tid; e < nfl / 2; e += THREADS)   // rows are 24 bytes: always 8-byte aligned
+                    reinterpret_cast<float2 *>(dst)[e] = reinterpret_cast<const float2 *>(stage)[e];
+            }
+        }
     }
     K2_STAMP(6);
     if (tid == 0) {
