@@ -299,8 +299,9 @@ int ysb_undo_letterbox(float *d_dets, const int32_t *d_det_cnt, int batch, int m
  *     use     [slots] u32 (completed uses of the slot, local)      err [1] u32 (a spin timed out, local)
  *   per step and slot, all on the caller's stream:
  *     ysb_gather_begin       zero the filter counters, tell every peer "I have consumed the previous use of this slot"
- *                            and wait until every peer has said the same (the slot may be overwritten)
- *     ysb_filter_candidates, ysb_select_nms_gather  (rows + counts -> every peer's slot, then arrival counts)
+ *                            (a remote store per peer, no waiting)
+ *     ysb_filter_candidates, ysb_select_nms_gather  (each image's CTA waits for the peers' acks of this slot -- sent a
+ *                            whole filter + NMS pass earlier -- then rows + counts -> every peer's slot, then arrival counts)
  *     ysb_gather_wait        wait until the rows of every rank have landed in MY slot
  *   Every rank must run the same sequence of (slot) steps.  Spins are bounded (~20 s); a timeout sets `err`, which
  *   ysb_gather_error reads back (host sync). */

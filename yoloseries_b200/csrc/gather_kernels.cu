@@ -5,7 +5,7 @@
 // lives in the NMS kernel (nms_kernel.cu: the ordered row write stores into every peer's slot and then adds one
 // system-scope arrival count per image); this file holds the buffer management and the two flow-control kernels:
 //   k_gather_begin  zero the filter counters of the step; publish "I am done reading the previous use of this slot"
-//                   (ack) to every peer; wait for the same from every peer -> the slot regions may be overwritten
+//                   (ack) to every peer.  The NMS kernel waits for the peers' acks before it overwrites their slots.
 //   k_gather_wait   wait until all images of every rank have landed in my slot; bump the slot's use counter
 // Spins are volatile loads of LOCAL memory that peers write remotely (the L2 is the point of coherence for incoming
 // NVLink writes), bounded by a wall-clock limit: a timeout sets the buffer's err word instead of hanging the GPU.
@@ -14,30 +14,6 @@
 #include "ysb_internal.cuh"
 
 namespace ysb {
-
-constexpr unsigned long long kSpinLimitNs = 20ull * 1000ull * 1000ull * 1000ull;
-
-__device__ __forceinline__ unsigned long long global_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-
-// wait until *p - target, as a signed 32-bit difference, is >= 0
-__device__ __forceinline__ bool spin_until_reached(const volatile unsigned int *p, unsigned int target)
-{
-    if (static_cast<int>(*p - target) >= 0) return true;
-    const unsigned long long t0 = global_ns();
-    for (;;) {
-#pragma unroll 1
-        for (int i = 0; i < 64; ++i) {
-            if (static_cast<int>(*p - target) >= 0) return true;
-            __nanosleep(64);
-        }
-        if (global_ns() - t0 > kSpinLimitNs) return false;
-    }
-}
 
 struct BeginArgs {
     int world, rank;
@@ -54,11 +30,10 @@ __global__ void __launch_bounds__(256) k_gather_begin(const __grid_constant__ Be
     for (long long i = threadIdx.x; i < a.n_counts; i += blockDim.x) a.counts[i] = 0;
     const unsigned int u = *a.use;   // uses of this slot that I have completely consumed (stream order)
     const int r = threadIdx.x;
-    if (r < a.world && r != a.rank) {
-        *reinterpret_cast<volatile unsigned int *>(a.peer_ack[r]) = u;   // remote store: "rank `rank` is done with use u"
-        __threadfence_system();
-        if (!spin_until_reached(a.my_ack + r, u)) atomicExch(a.err, 1u);
-    }
+    // remote store: "rank `rank` is done with use u of this slot".  Nobody waits here: the matching wait sits in the NMS
+    // kernel, right before its first store into a peer's slot (nms_kernel.cu), a whole filter + NMS pass later -- by then
+    // the peers' acks have long arrived and the step-start barrier this used to be costs nothing.
+    if (r < a.world && r != a.rank) *reinterpret_cast<volatile unsigned int *>(a.peer_ack[r]) = u;
 }
 
 struct WaitArgs {
@@ -102,6 +77,10 @@ bool make_gather_sink(const ysb_gather *g, int slot, GatherSink *out)
         out->cnt[r] = reinterpret_cast<int32_t *>(at(g->d_buf[r], L.cnt + L.cnt_slot * slot + L.cnt_rank * g->rank));
         out->arrived[r] = reinterpret_cast<unsigned int *>(at(g->d_buf[r], L.arrived)) + (static_cast<size_t>(slot) * g->world + g->rank);
     }
+    void *mine = g->d_buf[g->rank];
+    out->my_ack = reinterpret_cast<unsigned int *>(at(mine, L.ack)) + static_cast<size_t>(slot) * g->world;
+    out->use = reinterpret_cast<unsigned int *>(at(mine, L.use)) + slot;
+    out->err = reinterpret_cast<unsigned int *>(at(mine, L.err));
     return true;
 }
 

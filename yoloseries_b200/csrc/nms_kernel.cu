@@ -386,6 +386,8 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
             else if (G.world == 0) det_cnt[img] = -1;  // no survivor: the reference appends None
         }
         if (!ARRAY && G.world > 0 && tid < G.world) {   // detection gather: the count goes to every rank's slot
+            // peer `tid` must have consumed the previous use of this slot before its region is overwritten
+            if (tid != G.rank && !spin_until_reached(G.my_ack + tid, *G.use)) atomicExch(G.err, 1u);
             G.cnt[tid][img] = -1;
             __threadfence_system();
             atomicAdd_system(G.arrived[tid], 1u);
@@ -895,6 +897,9 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
         const int nfl = written * 6;
         const int nfl4 = (nfl + 3) & ~3;
         if (tid < nfl4 - nfl) stage[nfl + tid] = 0.0f;   // the last 16-byte store may reach past the rows: defined bytes
+        // detection gather: every peer must have consumed the previous use of this slot (its ack, published at the start
+        // of its current step, arrived long ago in the steady state) before anything is stored into its region
+        if (G.world > 0 && tid < G.world && tid != G.rank && !spin_until_reached(G.my_ack + tid, *G.use)) atomicExch(G.err, 1u);
         __syncthreads();
         const size_t img_off = static_cast<size_t>(img) * max_det * 6;
         const int ndst = G.world > 0 ? G.world : 1;

@@ -275,6 +275,11 @@ class ShardedPostProcessor:
         """The launch sequence of one batch on stream ``st`` (plain C-ABI calls: capturable into a CUDA graph)."""
         lib, sl, params = self.lib, self._slots[lane], self._ent["params"]
         sp = ctypes.c_void_p(st.cuda_stream)
+        if self.mode == "p2p":
+            # first thing of the step: tell the peers this slot's previous contents have been consumed (they check it
+            # right before storing into it, a filter + NMS pass from now)
+            g = ctypes.byref(self.dg.g)
+            _lib.check(lib.ysb_gather_begin(g, lane, None, 0, sp), "ysb_gather_begin")
         if events:
             events[0].record(st)
         _lib.check(lib.ysb_filter_candidates(ctypes.byref(params), ptrs, nheads, sl["keys"].data_ptr(), self._key_cap,
@@ -282,8 +287,6 @@ class ShardedPostProcessor:
         if events:
             events[1].record(st)
         if self.mode == "p2p":
-            g = ctypes.byref(self.dg.g)
-            _lib.check(lib.ysb_gather_begin(g, lane, None, 0, sp), "ysb_gather_begin")
             _lib.check(lib.ysb_select_nms_gather(ctypes.byref(params), ptrs, nheads, sl["keys"].data_ptr(), self._key_cap,
                                                  sl["counts"].data_ptr(), g, lane, sl["idx"].data_ptr(), sp),
                        "ysb_select_nms_gather")
