@@ -21,6 +21,8 @@
 // One CTA per image.  Two flavours of the CTA: 1024 threads (one image per SM: lowest latency, small batches) and 512
 // threads with <= 113 KB of shared memory (two images per SM: the barrier stalls of one overlap the work of the other;
 // batches larger than the SM count).
+#include <cstdlib>
+
 #include "ysb_internal.cuh"
 
 namespace ysb {
@@ -938,6 +940,18 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
 // CTAs' shared memory), else 1024 threads.  Profiling builds can force it (ysb_debug_set_nms_threads).
 static int g_force_threads = 0;
 void debug_set_nms_threads(int t) { g_force_threads = t; }
+#ifdef YSB_PROFILING_VARIANTS
+// profiling build only: YSB_NMS_THREADS=512|1024 forces the CTA flavour (read once)
+static int env_force_threads()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("YSB_NMS_THREADS");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+#endif
 
 static int device_sm_count()
 {
@@ -970,6 +984,9 @@ static cudaError_t launch_any(const Plan &P, const EXTRA &X, const uint64_t *d_k
     else memset(&G, 0, sizeof(G));
     const bool small_keep = P.max_det <= 320;
     int threads = (small_keep && P.batch > device_sm_count()) ? 512 : 1024;
+#ifdef YSB_PROFILING_VARIANTS
+    if (env_force_threads()) g_force_threads = env_force_threads();
+#endif
     if (g_force_threads == 512 && small_keep) threads = 512;
     if (g_force_threads == 1024) threads = 1024;
     if (!small_keep) return launch_flavour<EXTRA, 1024, 1024>(P, X, d_keys, key_cap, d_counts, d_dets, d_det_idx, d_det_cnt, stream, G);
