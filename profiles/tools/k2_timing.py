@@ -4,9 +4,10 @@ from yoloseries_b200 import synth, _lib
 from yoloseries_b200.engine import PostProcessor
 lib = _lib.load()
 fam = sys.argv[1] if len(sys.argv) > 1 else "yolov5"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 dists = ("dense", "sparse", "crowd") if fam == "yolov5" else ("dense", "sparse")
 for dist in dists:
-    heads = synth.make_heads(fam, 64, 640, 640, 80, dist, 1234, "cuda")
+    heads = synth.make_heads(fam, B, 640, 640, 80, dist, 1234, "cuda")
     hyp = synth.map_profile_hyp()
     if fam == "fcos":
         hyp.update(cls_threshold=0.2, iou_threshold=0.35, max_predictions_per_img=100)
@@ -22,5 +23,5 @@ for dist in dists:
     names = ["select", "gather", "sort", "(setup)", "decode+nms", "postfilter", "emit"]
     names = ["select(hist)", "gather", "sort", "nms(+decode)", "postfilter", "emit"]
     acc = t[:, 8:13].mean(axis=0) / 1.9 / 1000
-    print(dist, "nms breakdown: decode=%.1f phaseA=%.1f phaseB=%.1f phaseC=%.1f append=%.1f us" % tuple(acc))
+    print(fam, B, dist, "nms breakdown: decode=%.1f phaseA=%.1f phaseB=%.1f phaseC=%.1f append=%.1f us" % tuple(acc))
     print(dist, " ".join(f"{n}={v/1000:.1f}us" for n, v in zip(names, d.mean(axis=0))), "total=%.1fus" % ((t[:, 6] - t[:, 0]).mean() / 1.9 / 1000))

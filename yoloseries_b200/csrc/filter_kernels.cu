@@ -407,6 +407,40 @@ __device__ __forceinline__ void cp_async_wait()
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// mbarrier + bulk-copy (TMA engine) helpers
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src_gmem, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src_gmem), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
 #ifdef YSB_PROFILING_VARIANTS
 #include "filter_variants.cuh"
 #endif
@@ -418,6 +452,79 @@ __device__ __forceinline__ void cp_async_wait()
 // even float stride are walked with a per-thread rotation so that the 32 rows a warp scans sit in 32 different banks.
 // -------------------------------------------------------------------------------------------------------
 constexpr int kRowsTile = 128;
+
+// One thread scans one staged row (thread t of the tile -> row r0 + t of level lv), decides it and the warp appends the
+// survivors.  Every thread of the warp must call (rows beyond nrows contribute nothing).
+__device__ __forceinline__ void rows_scan_emit(const Plan &P, const LevelDesc &lv, int img, const float *tile, int sstride,
+                                               int nrows, int r0, int t, uint64_t *__restrict__ keys, int64_t key_cap,
+                                               int32_t *__restrict__ counts)
+{
+    uint64_t out[1] = {0ull};
+    unsigned okm = 0u;
+    int npre = 0;
+    uint32_t smax_bits = 0u, smin_inv = 0u;
+    if (t < nrows) {
+        const float *row = tile + t * sstride;
+        const float *cls = row + P.cls_col_in;
+        float m1 = -INFINITY, m2 = -INFINITY;
+        int k0 = 0;
+        // thread t reads word sstride*t + k: conflict-free when sstride is odd; otherwise start the walk at column t so
+        // that the 32 lanes hit (sstride+1)*t + k.  The visiting order is irrelevant: a unique maximum has a unique
+        // index, and equal maxima force m2 == m1, i.e. the literal path, which walks in index order.
+        if (sstride & 1) {
+            // odd stride (YOLOv7's 85-float rows): already conflict-free, a straight run without the wrap test
+#pragma unroll 8
+            for (int k = 0; k < P.C; ++k) top2_update(cls[k], k, m1, m2, k0);
+        } else {
+            // rotated walk: lane l starts at column l, i.e. reads word sstride*tid + l + t = (sstride + 1)*l + t (mod 32)
+            // -- an odd multiplier, conflict-free.  Every lane runs the same C iterations (two straight runs per lane
+            // would diverge); the first C - 32 of them cannot wrap, so only the last 32 carry the wrap test.
+            const int lane = t & 31;
+            if (P.C >= 32) {
+                const int straight = P.C - 32;
+#pragma unroll 8
+                for (int t = 0; t < straight; ++t) top2_update(cls[t + lane], t + lane, m1, m2, k0);
+                int k = straight + lane;
+#pragma unroll 8
+                for (int t = 0; t < 32; ++t) {
+                    if (k >= P.C) k -= P.C;
+                    top2_update(cls[k], k, m1, m2, k0);
+                    ++k;
+                }
+            } else {
+                int k = lane % P.C;
+                for (int t = 0; t < P.C; ++t) {
+                    top2_update(cls[k], k, m1, m2, k0);
+                    if (++k == P.C) k = 0;
+                }
+            }
+        }
+        const int cand = lv.cand_off + r0 + t;
+        float objv = 0.0f;
+        if (P.use_obj) {
+            if (P.obj_src == 1)  // RetinaNet-exp: conf logit is the last column of the reg tensor
+                objv = __ldg(P.lv[0].p1 + (static_cast<size_t>(img) * P.N + cand) * P.reg_row_w + 4);
+            else
+                objv = row[P.obj_col_in];
+        }
+        float score;
+        int c;
+        bool pre, ok;
+        if (P.input_kind == YSB_INPUT_DECODED_ROWS)
+            ok = decide_candidate<true>(P, m1, m2, k0, objv, [&](int kk) { return cls[kk]; }, score, c, pre);
+        else
+            ok = decide_candidate<false>(P, m1, m2, k0, objv, [&](int kk) { return cls[kk]; }, score, c, pre);
+        npre = pre ? 1 : 0;
+        if (ok) {
+            out[0] = pack_key(score, static_cast<uint32_t>(P.cand_base + cand), static_cast<uint32_t>(c));
+            okm = 1u;
+            smax_bits = __float_as_uint(score);
+            smin_inv = ~smax_bits;
+        }
+    }
+    emit_keys<1>(out, okm, npre, smax_bits, smin_inv, keys + static_cast<int64_t>(img) * key_cap, key_cap,
+                 counts + img * 4, P.pre_kind == PRE_ANY_GT);
+}
 
 __global__ void __launch_bounds__(kRowsTile) k_filter_rows(const __grid_constant__ Plan P, uint64_t *__restrict__ keys,
                                                            int64_t key_cap, int32_t *__restrict__ counts)
@@ -455,71 +562,104 @@ __global__ void __launch_bounds__(kRowsTile) k_filter_rows(const __grid_constant
     }
     __syncthreads();
 
-    uint64_t out[1] = {0ull};
-    unsigned okm = 0u;
-    int npre = 0;
-    uint32_t smax_bits = 0u, smin_inv = 0u;
-    if (static_cast<int>(threadIdx.x) < nrows) {
-        const float *row = tile + threadIdx.x * sstride;
-        const float *cls = row + P.cls_col_in;
-        float m1 = -INFINITY, m2 = -INFINITY;
-        int k0 = 0;
-        // thread t reads word sstride*t + k: conflict-free when sstride is odd; otherwise start the walk at column t so
-        // that the 32 lanes hit (sstride+1)*t + k.  The visiting order is irrelevant: a unique maximum has a unique
-        // index, and equal maxima force m2 == m1, i.e. the literal path, which walks in index order.
-        if (sstride & 1) {
-            // odd stride (YOLOv7's 85-float rows): already conflict-free, a straight run without the wrap test
-#pragma unroll 8
-            for (int k = 0; k < P.C; ++k) top2_update(cls[k], k, m1, m2, k0);
+    rows_scan_emit(P, lv, img, tile, sstride, nrows, r0, static_cast<int>(threadIdx.x), keys, key_cap, counts);
+}
+
+// -------------------------------------------------------------------------------------------------------
+// rows layout, persistent ring version (the default whenever the tensors are 16-byte aligned -- every reference layout).
+// A tile of 128 rows is ONE contiguous block of memory (40-44 KB), i.e. one bulk copy of the TMA engine
+// (cp.async.bulk -> mbarrier complete_tx): a CTA keeps kRingStages tiles in flight / under the scan, thread 0 re-arms a
+// stage as soon as the CTA has finished reading it.  Against k_filter_rows (one tile per CTA: ~300 CTA launches per SM
+// for a RetinaNet batch, 20 cp.async per thread and tile, no copy/scan overlap inside a CTA) this removes the per-tile
+// CTA turnaround and the load-issue instructions.  Work item w -> (image w % batch, unit w / batch): image fastest, so
+// CTAs that run at the same time append to different images' counters.
+// -------------------------------------------------------------------------------------------------------
+constexpr int kRingStages = 2;
+
+__global__ void __launch_bounds__(kRowsTile) k_filter_rows_ring(const __grid_constant__ Plan P, uint64_t *__restrict__ keys,
+                                                                int64_t key_cap, int32_t *__restrict__ counts)
+{
+    extern __shared__ __align__(128) float ring[];          // kRingStages tiles of 128 * (row_w_in | 1) floats
+    __shared__ __align__(8) uint64_t full_bar[kRingStages];
+    const int tid = static_cast<int>(threadIdx.x);
+    const int rw = P.row_w_in;
+    const int stage_floats = kRowsTile * (rw | 1);
+    const long long total = static_cast<long long>(P.batch) * P.units_per_img;
+    const long long G = gridDim.x;
+
+    struct Unit {
+        const LevelDesc *lv;
+        const float *src;
+        int img, r0, nrows;
+        bool bulk;   // whole tile is a multiple of 16 bytes: one bulk copy; else plain loads at consumption time
+    };
+    auto unit_of = [&](long long w) {
+        Unit u;
+        u.img = static_cast<int>(w % P.batch);
+        const int t = static_cast<int>(w / P.batch);
+        int l = 0;
+#pragma unroll
+        for (int i = 1; i < YSB_MAX_LEVELS; ++i)
+            if (i < P.L && t >= P.lv[i].unit_off) l = i;
+        u.lv = &P.lv[l];
+        const int rows_l = (l + 1 < P.L ? P.lv[l + 1].cand_off : P.N) - u.lv->cand_off;
+        u.r0 = (t - u.lv->unit_off) * kRowsTile;
+        u.nrows = min(kRowsTile, rows_l - u.r0);
+        u.src = u.lv->p0 + (static_cast<size_t>(u.img) * u.lv->img_rows + u.r0) * rw;
+        u.bulk = ((u.nrows * rw) & 3) == 0 && (reinterpret_cast<uintptr_t>(u.src) & 15u) == 0;
+        return u;
+    };
+    auto arm = [&](long long w, int s) {   // thread 0: one arrival (+ the tile's bytes) completes the stage's phase
+        const Unit u = unit_of(w);
+        const uint32_t bar = smem_u32(&full_bar[s]);
+        if (u.bulk) {
+            const uint32_t bytes = static_cast<uint32_t>(u.nrows * rw) * 4u;
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(smem_u32(ring + static_cast<size_t>(s) * stage_floats), u.src, bytes, bar);
         } else {
-            // rotated walk: lane l starts at column l, i.e. reads word sstride*tid + l + t = (sstride + 1)*l + t (mod 32)
-            // -- an odd multiplier, conflict-free.  Every lane runs the same C iterations (two straight runs per lane
-            // would diverge); the first C - 32 of them cannot wrap, so only the last 32 carry the wrap test.
-            const int lane = static_cast<int>(threadIdx.x) & 31;
-            if (P.C >= 32) {
-                const int straight = P.C - 32;
-#pragma unroll 8
-                for (int t = 0; t < straight; ++t) top2_update(cls[t + lane], t + lane, m1, m2, k0);
-                int k = straight + lane;
-#pragma unroll 8
-                for (int t = 0; t < 32; ++t) {
-                    if (k >= P.C) k -= P.C;
-                    top2_update(cls[k], k, m1, m2, k0);
-                    ++k;
-                }
-            } else {
-                int k = lane % P.C;
-                for (int t = 0; t < P.C; ++t) {
-                    top2_update(cls[k], k, m1, m2, k0);
-                    if (++k == P.C) k = 0;
-                }
-            }
+            mbar_arrive(bar);
         }
-        const int cand = lv.cand_off + r0 + threadIdx.x;
-        float objv = 0.0f;
-        if (P.use_obj) {
-            if (P.obj_src == 1)  // RetinaNet-exp: conf logit is the last column of the reg tensor
-                objv = __ldg(P.lv[0].p1 + (static_cast<size_t>(img) * P.N + cand) * P.reg_row_w + 4);
-            else
-                objv = row[P.obj_col_in];
-        }
-        float score;
-        int c;
-        bool pre, ok;
-        if (P.input_kind == YSB_INPUT_DECODED_ROWS)
-            ok = decide_candidate<true>(P, m1, m2, k0, objv, [&](int kk) { return cls[kk]; }, score, c, pre);
-        else
-            ok = decide_candidate<false>(P, m1, m2, k0, objv, [&](int kk) { return cls[kk]; }, score, c, pre);
-        npre = pre ? 1 : 0;
-        if (ok) {
-            out[0] = pack_key(score, static_cast<uint32_t>(P.cand_base + cand), static_cast<uint32_t>(c));
-            okm = 1u;
-            smax_bits = __float_as_uint(score);
-            smin_inv = ~smax_bits;
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kRingStages; ++s) mbar_init(smem_u32(&full_bar[s]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kRingStages; ++s) {
+            const long long w = blockIdx.x + s * G;
+            if (w < total) arm(w, s);
         }
     }
-    emit_keys<1>(out, okm, npre, smax_bits, smin_inv, keys + static_cast<int64_t>(img) * key_cap, key_cap,
-                 counts + img * 4, P.pre_kind == PRE_ANY_GT);
+    int k = 0;
+    for (long long w = blockIdx.x; w < total; w += G, ++k) {
+        const int s = k % kRingStages;
+        const uint32_t phase = static_cast<uint32_t>(k / kRingStages) & 1u;
+        const Unit u = unit_of(w);
+        float *tile = ring + static_cast<size_t>(s) * stage_floats;
+        mbar_wait(smem_u32(&full_bar[s]), phase);
+        int sstride = rw;
+        if (!u.bulk) {   // odd shapes (CTA-uniform): scalar loads into a tile padded to an odd stride
+            sstride = rw | 1;
+            const int nfl = u.nrows * rw;
+            for (int e = tid; e < nfl; e += kRowsTile) {
+                const int row = e / rw, col = e - row * rw;
+                tile[row * sstride + col] = ldg_stream1(u.src + e);
+            }
+            __syncthreads();
+        }
+        rows_scan_emit(P, *u.lv, u.img, tile, sstride, u.nrows, u.r0, tid, keys, key_cap, counts);
+        __syncthreads();   // every thread is done reading the stage
+        if (tid == 0) {
+            const long long wn = w + kRingStages * G;
+            // (generic-proxy stores of an odd-shaped tile are ordered before the engine's next write into the stage)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (wn < total) arm(wn, s);
+        }
+    }
 }
 
 // -------------------------------------------------------------------------------------------------------
@@ -673,6 +813,23 @@ cudaError_t launch_filter(const Plan &P, int vec, uint64_t *d_keys, int64_t key_
         }
     } else {
         const size_t smem = static_cast<size_t>(kRowsTile) * (P.row_w_in | 1) * sizeof(float);
+        // persistent ring kernel when two CTAs with kRingStages tiles each fit an SM and the tensors allow bulk copies
+        // (16-byte aligned bases, image strides that keep every image's first row 16-byte aligned)
+        bool ring_ok = kRingStages * smem <= 110u * 1024u;
+        for (int l = 0; l < P.L && ring_ok; ++l)
+            ring_ok = (reinterpret_cast<uintptr_t>(P.lv[l].p0) & 15u) == 0 &&
+                      ((static_cast<long long>(P.lv[l].img_rows) * P.row_w_in) & 3) == 0;
+        if (ring_ok) {
+            const size_t rsmem = kRingStages * smem;
+            e = cudaFuncSetAttribute(k_filter_rows_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rsmem));
+            if (e != cudaSuccess) return e;
+            int dev = 0, sms = 148;
+            if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            const long long total = static_cast<long long>(P.batch) * P.units_per_img;
+            const long long slots = static_cast<long long>(sms) * (rsmem <= 74u * 1024u ? 3 : 2);
+            k_filter_rows_ring<<<static_cast<unsigned>(total < slots ? total : slots), kRowsTile, rsmem, stream>>>(P, d_keys, key_cap, d_counts);
+            return cudaGetLastError();
+        }
         if (smem > 48 * 1024) {
             e = cudaFuncSetAttribute(k_filter_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
             if (e != cudaSuccess) return e;

@@ -29,7 +29,8 @@ namespace ysb {
 
 constexpr int kTranche = 2048;      // keys selected, sorted and walked at a time
 constexpr int kMinTranche = 512;    // a tranche smaller than this is only taken when nothing else is left
-constexpr int kSampleTarget = 640;  // tranche size aimed at when the threshold comes from a sample
+constexpr int kSampleTarget = 1024; // size a later tranche is aimed at when its threshold comes from a sample
+template <int THREADS> constexpr int kFirstTarget = THREADS >= 1024 ? 640 : (THREADS * 13) / 16;  // first tranche
 constexpr int kDigitBits = 11;
 constexpr int kBins = 1 << kDigitBits;
 constexpr int kChunk = 128;         // candidates resolved per step of the greedy walk
@@ -229,6 +230,54 @@ __device__ uint64_t select_lower_bound(NmsSmem<KEEP> &S, const uint64_t *__restr
     }
 }
 
+// Block-wide gather of the keys with lo <= norm_key <= hi_incl into S.keys[at0 ...) (arrival order); returns at0 + their
+// count (entries beyond kTranche are counted, not stored).  One pass over the image's key list.
+template <int THREADS, int KEEP>
+__device__ int gather_range(NmsSmem<KEEP> &S, const uint64_t *__restrict__ keys, int M, uint32_t smin, uint64_t lo,
+                            uint64_t hi_incl, int at0)
+{
+    const int tid = threadIdx.x;
+    if (tid == 0) S.n_sel = at0;
+    __syncthreads();
+    for (int i0 = 0; i0 < M; i0 += kKeyBatch * THREADS) {
+        uint64_t kk[kKeyBatch];
+#pragma unroll
+        for (int q = 0; q < kKeyBatch; ++q) {
+            const int i = i0 + q * THREADS + tid;
+            kk[q] = i < M ? __ldg(keys + i) : 0ull;
+        }
+        // one shared-memory reservation per warp and batch (a reservation per ballot serialised ~M/32 atomics on one
+        // address: with ~8 % of the keys selected nearly every ballot is non-empty)
+        unsigned bal[kKeyBatch];
+        int warp_total = 0;
+#pragma unroll
+        for (int q = 0; q < kKeyBatch; ++q) {
+            const uint64_t nk = norm_key(kk[q], smin);
+            const bool in = (i0 + q * THREADS + tid < M) && nk >= lo && nk <= hi_incl;
+            bal[q] = __ballot_sync(0xffffffffu, in);
+            warp_total += __popc(bal[q]);
+        }
+        if (warp_total) {
+            int base = 0;
+            if ((tid & 31) == 0) base = atomicAdd(&S.n_sel, warp_total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const unsigned below = (1u << (tid & 31)) - 1u;
+#pragma unroll
+            for (int q = 0; q < kKeyBatch; ++q) {
+                if ((bal[q] >> (tid & 31)) & 1u) {
+                    const int at = base + __popc(bal[q] & below);
+                    if (at < kTranche) S.keys[at] = kk[q];
+                }
+                base += __popc(bal[q]);
+            }
+        }
+    }
+    __syncthreads();
+    const int n = S.n_sel;
+    __syncthreads();
+    return n;
+}
+
 // Descending sort of keys[0..n) (n <= THREADS*E) by a bitonic network held in registers: element i = tid + THREADS*r
 // lives in register r of thread tid.  Strides >= THREADS are thread-local, strides < 32 use warp shuffles, only strides
 // 32..THREADS/2 go through shared memory.  Slots beyond n sort as 0 (smaller than any real key).
@@ -368,7 +417,7 @@ __device__ __forceinline__ void decode_boxes(NmsSmem<KEEP> &S, const Plan &P, co
 // EXTRA = NoExtraPasses (one set of heads) or ExtraPasses (TTA: boxes are decoded from the pass a candidate came from;
 // thresholds / NMS settings are those of P, identical in every pass).
 template <bool ARRAY, typename EXTRA, int THREADS, int KEEP>
-__global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2)
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, const uint64_t *__restrict__ keys_all,
              int64_t key_cap, const int32_t *__restrict__ counts, float *__restrict__ dets,
              int32_t *__restrict__ det_idx, int32_t *__restrict__ det_cnt, const ArrayArgs aa,
@@ -409,6 +458,8 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
     const bool window = !ARRAY && P.postprocess_bbox && M > 1 && M < P.window_hi;
 
     int kept = 0, processed = 0, n_tranche = 0, decoded_upto = 0;
+    bool whole = false;   // the (single) tranche in shared memory holds every survivor
+    uint64_t last_lo = 0; // lower bound of the last tranche's normalised keys
     uint64_t hi_incl = ~0ull;
     for (;;) {
         K2_STAMP(0);
@@ -419,48 +470,29 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
         uint64_t lo = 0;
         int n = 0;
         const int remaining = M - processed;
+        // First tranche: aimed at what ONE sort element per thread holds (most images reach max_det inside it, and the
+        // bitonic network over THREADS slots costs less than half of the next size); if the walk needs more, the later
+        // tranches are large (fewer passes over the key list).
+        const bool first = processed == 0;
+        const int take_all = first ? THREADS : kTranche;       // this many keys or fewer: no selection pass
+        const int target = first ? kFirstTarget<THREADS> : kSampleTarget;
         int stride = remaining > 4 * kTranche ? (remaining >= 32 * kTranche ? 32 : remaining / kTranche) : 1;
         for (;;) {
-            if (remaining > kTranche) {
-                const int want = stride > 1 ? (kSampleTarget + stride - 1) / stride : kMinTranche;
-                const int cap = stride > 1 ? (kTranche * 3 / 4) / stride : kTranche;
+            if (remaining > take_all) {
+                const int want = stride > 1 ? (target + stride - 1) / stride : (first ? target : kMinTranche);
+                const int cap = stride > 1 ? (first ? THREADS : kTranche * 3 / 4) / stride : (first ? THREADS : kTranche);
                 lo = select_lower_bound<THREADS, KEEP>(S, keys, M, smin, hi_incl, nbits, stride, want, cap);
             }
             K2_STAMP(1);
-            if (tid == 0) S.n_sel = 0;
-            __syncthreads();
             // ---- gather {lo <= nk <= hi_incl}: one exact pass over the key list -----------------------------------
-            for (int i0 = 0; i0 < M; i0 += kKeyBatch * THREADS) {
-                uint64_t kk[kKeyBatch];
-#pragma unroll
-                for (int q = 0; q < kKeyBatch; ++q) {
-                    const int i = i0 + q * THREADS + tid;
-                    kk[q] = i < M ? __ldg(keys + i) : 0ull;
-                }
-#pragma unroll
-                for (int q = 0; q < kKeyBatch; ++q) {
-                    const uint64_t nk = norm_key(kk[q], smin);
-                    const bool in = (i0 + q * THREADS + tid < M) && nk >= lo && nk <= hi_incl;
-                    const unsigned bal = __ballot_sync(0xffffffffu, in);
-                    if (bal) {
-                        int base = 0;
-                        if ((tid & 31) == 0) base = atomicAdd(&S.n_sel, __popc(bal));
-                        base = __shfl_sync(0xffffffffu, base, 0);
-                        if (in) {
-                            const int at = base + __popc(bal & ((1u << (tid & 31)) - 1u));
-                            if (at < kTranche) S.keys[at] = kk[q];
-                        }
-                    }
-                }
-            }
-            __syncthreads();
-            n = S.n_sel;
-            __syncthreads();
+            n = gather_range<THREADS, KEEP>(S, keys, M, smin, lo, hi_incl, 0);
             if (n <= kTranche) break;
             stride = 1;  // the sampled threshold let too many keys through: redo with exact counts
         }
         K2_STAMP(2);
         n_tranche = n;
+        whole = processed == 0 && n == M;
+        last_lo = lo;
         // ---- 2. sort descending -----------------------------------------------------------------------------------
         sort_tranche<THREADS>(S.keys, n);
         const int n_use = min(n, limit - processed);
@@ -652,7 +684,13 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
         // Every survivor counts, not only the ones the walk visited: they are streamed in blocks of kTranche -- the
         // (single, sorted) tranche still in shared memory when it holds them all, the image's key list otherwise.
         const int warp = tid >> 5, lane = tid & 31;
-        const bool resident = M <= kTranche;            // then n_tranche == M and S.keys / S.raw[0..decoded_upto) are valid
+        // One tranche was walked and the rest of the survivors fits next to it: append them (unordered -- the count filter
+        // does not care) instead of streaming and re-decoding the whole list.
+        if (!whole && processed == n_tranche && M <= kTranche && !P.topk_sqrt && last_lo > 0) {
+            n_tranche = gather_range<THREADS, KEEP>(S, keys, M, smin, 0ull, last_lo - 1, n_tranche);
+            whole = n_tranche == M;
+        }
+        const bool resident = whole;                    // then n_tranche == M and S.keys / S.raw[0..decoded_upto) are valid
         const int total = resident ? min(n_tranche, limit) : M;   // FCOS (top-k) only ever gets here with M <= 300
         for (int r = tid; r < kept; r += THREADS) {
             S.kept_cnt[r] = 0;
@@ -936,8 +974,7 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
-// CTA flavour: 512 threads x 2 per SM when there are more images than SMs (and the kept list is short enough for two
-// CTAs' shared memory), else 1024 threads.  Profiling builds can force it (ysb_debug_set_nms_threads).
+// CTA flavour (launch_any): 512 or 1024 threads.  Profiling builds can force it (ysb_debug_set_nms_threads).
 static int g_force_threads = 0;
 void debug_set_nms_threads(int t) { g_force_threads = t; }
 #ifdef YSB_PROFILING_VARIANTS
@@ -970,7 +1007,19 @@ static cudaError_t launch_flavour(const Plan &P, const EXTRA &X, const uint64_t 
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(NmsSmem<KEEP>)));
     if (e != cudaSuccess) return e;
     ArrayArgs aa{};
-    kern<<<P.batch, THREADS, sizeof(NmsSmem<KEEP>), stream>>>(P, X, d_keys, key_cap, d_counts, d_dets, d_det_idx, d_det_cnt, aa, G);
+    size_t smem = sizeof(NmsSmem<KEEP>);
+#ifdef YSB_PROFILING_VARIANTS
+    {   // profiling build only: YSB_NMS_SMEM=<bytes> requests more shared memory (limits the CTAs per SM)
+        static long pad = -1;
+        if (pad < 0) { const char *e = getenv("YSB_NMS_SMEM"); pad = e ? atol(e) : 0; }
+        if (static_cast<size_t>(pad) > smem) {
+            smem = static_cast<size_t>(pad);
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (e != cudaSuccess) return e;
+        }
+    }
+#endif
+    kern<<<P.batch, THREADS, smem, stream>>>(P, X, d_keys, key_cap, d_counts, d_dets, d_det_idx, d_det_cnt, aa, G);
     return cudaGetLastError();
 }
 
@@ -983,7 +1032,14 @@ static cudaError_t launch_any(const Plan &P, const EXTRA &X, const uint64_t *d_k
     if (sink) G = *sink;
     else memset(&G, 0, sizeof(G));
     const bool small_keep = P.max_det <= 320;
-    int threads = (small_keep && P.batch > device_sm_count()) ? 512 : 1024;
+    // 512 threads: the CTA leaves half of its SM's registers to three filter CTAs of the batches that follow, and two of
+    // them fit an SM when there are more images than SMs.  1024 threads: lowest latency per image -- small batches, the
+    // YOLOv8 DFL box decode (THREADS / 4 boxes per DRAM round trip) and very long key lists, whose selection passes
+    // scale with M / THREADS.  Measured on B200, 4 batches in flight, images/s 1024 -> 512 threads: YOLOv5s b=64 674 k ->
+    // 738 k, YOLOv7 b=64 584 k -> 623 k, b=8 451 k -> 397 k, YOLOv8 b=64 452 k -> 442 k, RetinaNet (76 725) 208 k -> 204 k.
+    const bool dfl = P.family == YSB_YOLOV8 && P.input_kind == YSB_INPUT_RAW_HEADS;
+    int threads = 1024;
+    if (small_keep && (P.batch > device_sm_count() || (P.batch >= 32 && !dfl && P.N <= 32768))) threads = 512;
 #ifdef YSB_PROFILING_VARIANTS
     if (env_force_threads()) g_force_threads = env_force_threads();
 #endif
