@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define YSB_ABI_VERSION 4
+#define YSB_ABI_VERSION 5
 #define YSB_MAX_LEVELS 8
 #define YSB_MAX_ANCHORS 9
 #define YSB_MAX_PASSES 4             /* test-time-augmentation passes merged by ysb_postprocess_tta */
@@ -249,6 +249,12 @@ int ysb_wbf_collect(const float *d_decoded, int batch, int64_t rows, int row_wid
  * d_mismatches (2) uint64: {values where the guarded routine differs, values where the branch-free batch variant differs
  * or mis-flags its out-of-range case}.  Both must come back 0. */
 int ysb_selftest_reciprocal(uint64_t *d_mismatches, void *stream);
+
+/* Tuning / test hook: CTA flavour of the selection + NMS kernel.  0 (default): chosen per call from the batch size and the
+ * family (csrc/nms_kernel.cu, launch_any); 512 / 1024: forced (512 only applies while max_det <= 320).  Both flavours give
+ * bit-identical results (tests/test_gpu_edge.py::test_nms_cta_flavours_agree_with_the_oracle).  Process-wide, not
+ * thread-safe: meant for A/B measurements and tests.  No reference counterpart. */
+int ysb_set_nms_cta_threads(int threads);
 
 /* mAP hand-off (the consumer of the kept rows, val_yolov5.py:388 -> utils/mAP.py).
  * ysb_map_iou: utils/mAP.py:18-42 `iou(box1, box2)` -- rows of row_w1 / row_w2 values whose first four are

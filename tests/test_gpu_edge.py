@@ -158,6 +158,27 @@ def test_full_size_properties(family, img, batch, dist):
         assert not np.any(iou >= hyp["iou_threshold"])
 
 
+@pytest.mark.parametrize("family,img,dist", [("yolov5", 640, "dense"), ("yolov5", 640, "sparse"), ("yolov5", 640, "crowd"),
+                                             ("yolov7", 320, "crowd"), ("yolox", 640, "dense"), ("yolox", 640, "sparse"),
+                                             ("fcos", 512, "dense"), ("retinanet", 320, "dense")])
+def test_nms_cta_flavours_agree_with_the_oracle(family, img, dist):
+    """The NMS kernel has a 512-thread and a 1024-thread CTA flavour (picked by batch size, csrc/nms_kernel.cu
+    launch_any) whose first tranche, sort width and post-filter path differ: both are forced here on the same inputs and
+    each must reproduce the oracle's rows and candidate indices bit for bit."""
+    from yoloseries_b200 import _lib, synth
+    hyp = oracle.default_hyp()
+    if family == "fcos":
+        hyp.update(cls_threshold=0.2, iou_threshold=0.35, max_predictions_per_img=100)
+    heads = synth.make_heads(family, 2, img, img, 80, dist, seed=77, device="cuda")
+    lib = _lib.load()
+    try:
+        for threads in (512, 1024):
+            assert lib.ysb_set_nms_cta_threads(threads) == 0
+            _check_against_oracle(family, heads, img, img, hyp)
+    finally:
+        lib.ysb_set_nms_cta_threads(0)
+
+
 def test_empty_batch_returns_empty_list():
     pp = _pp("yolov5", oracle.default_hyp())
     heads = [torch.zeros((0, 255, s, s), device="cuda") for s in (8, 4, 2)]

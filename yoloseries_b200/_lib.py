@@ -24,7 +24,7 @@ IOU_NUMBA_F64MIX, IOU_F32, GIOU, DIOU, CIOU = range(5)
 IOU_KIND_IDS = {"numba": IOU_NUMBA_F64MIX, "iou": IOU_F32, "giou": GIOU, "diou": DIOU, "ciou": CIOU}
 CMP_GE, CMP_GT = 0, 1
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 YSB_MAX_PASSES = 4
 YSB_MAX_PEERS = 16
 YSB_IPC_HANDLE_BYTES = 64
@@ -137,6 +137,7 @@ _SIGNATURES = {
                                        ctypes.c_int, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_float), ctypes.c_int,
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     "ysb_selftest_reciprocal": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "ysb_set_nms_cta_threads": (ctypes.c_int, [ctypes.c_int]),
     "ysb_map_iou": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
                                    ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "ysb_compute_tp_workspace_bytes": (ctypes.c_int, [ctypes.c_int64, ctypes.POINTER(ctypes.c_size_t)]),

@@ -743,9 +743,15 @@ int ysb_elementwise_iou(const float *d_b1, int64_t n1, const float *d_b2, int64_
     return cuda_status(launch_elementwise_iou(d_b1, n1, d_b2, n2, iou_kind, d_out, static_cast<cudaStream_t>(stream)));
 }
 
+int ysb_set_nms_cta_threads(int threads)
+{
+    if (threads != 0 && threads != 512 && threads != 1024) return YSB_ERR_BAD_ARG;
+    ysb::debug_set_nms_threads(threads);
+    return YSB_OK;
+}
+
 #ifdef YSB_K2_TIMING
 int ysb_debug_k2_timing(long long *host_out) { return cuda_status(ysb::debug_k2_timing(host_out)); }
-int ysb_debug_set_nms_threads(int t) { ysb::debug_set_nms_threads(t); return YSB_OK; }
 #endif
 
 }  // extern "C"

@@ -447,9 +447,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src_gmem
 
 // -------------------------------------------------------------------------------------------------------
 // rows layout (channels-last heads: YOLOv7, RetinaNet cls; and the decoded (b, N, C') tensor of any family).
-// A CTA stages a tile of 128 whole rows in shared memory with cp.async (rows are 340 B / 320 B and only 4-byte
-// aligned individually, but the tile is contiguous and 16-byte aligned), then one thread scans one row; rows with an
-// even float stride are walked with a per-thread rotation so that the 32 rows a warp scans sit in 32 different banks.
+// A CTA stages a tile of 128 whole rows in shared memory with one bulk copy (rows are 340 B / 320 B and only 4-byte
+// aligned individually, but the tile is contiguous and 16-byte aligned), then one thread scans one row: 128-bit shared
+// loads when the class run of every row is 16-byte aligned, else scalar loads; rows with an even stride are walked with
+// a per-thread rotation so that the rows a warp scans sit in different banks.
 // -------------------------------------------------------------------------------------------------------
 constexpr int kRowsTile = 128;
 
@@ -457,7 +458,7 @@ constexpr int kRowsTile = 128;
 // survivors.  Every thread of the warp must call (rows beyond nrows contribute nothing).
 __device__ __forceinline__ void rows_scan_emit(const Plan &P, const LevelDesc &lv, int img, const float *tile, int sstride,
                                                int nrows, int r0, int t, uint64_t *__restrict__ keys, int64_t key_cap,
-                                               int32_t *__restrict__ counts)
+                                               int32_t *__restrict__ counts, bool vec4 = false)
 {
     uint64_t out[1] = {0ull};
     unsigned okm = 0u;
@@ -471,7 +472,38 @@ __device__ __forceinline__ void rows_scan_emit(const Plan &P, const LevelDesc &l
         // thread t reads word sstride*t + k: conflict-free when sstride is odd; otherwise start the walk at column t so
         // that the 32 lanes hit (sstride+1)*t + k.  The visiting order is irrelevant: a unique maximum has a unique
         // index, and equal maxima force m2 == m1, i.e. the literal path, which walks in index order.
-        if (sstride & 1) {
+        if (vec4 && ((sstride | P.cls_col_in | P.C) & 3) == 0) {
+            // 16-byte aligned class runs (RetinaNet's 80-float rows, 84-float decoded rows): 128-bit shared loads, four
+            // independent (max, runner-up, position) chains -- one per float4 component -- that share the float4's
+            // position, merged at the end.  A quarter-warp reads 8 float4 per wavefront: with an even number of float4 per
+            // row the lanes start at float4 `lane & 7` (8 consecutive rows then sit in 8 different 16-byte bank groups), with an
+            // odd number the straight walk already is conflict-free.  Visiting order and chain split cannot change the
+            // result: a unique maximum has one position, and equal maxima -- within a chain or across chains -- surface
+            // as runner-up == maximum, i.e. the literal path below.
+            const int nq = P.C >> 2, R = sstride >> 2;
+            const float4 *c4 = reinterpret_cast<const float4 *>(cls);
+            float a1[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, a2[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            int aq[4] = {0, 0, 0, 0};
+            int q = (R & 1) ? 0 : (t & 7) % nq;   // 128-bit loads are served a quarter-warp at a time
+#pragma unroll 4
+            for (int s = 0; s < nq; ++s) {
+                const float4 v = c4[q];
+                const float c[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    a2[j] = fmaxf(a2[j], fminf(a1[j], c[j]));
+                    aq[j] = (c[j] > a1[j]) ? q : aq[j];
+                    a1[j] = fmaxf(a1[j], c[j]);
+                }
+                if (++q == nq) q = 0;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                m2 = fmaxf(fmaxf(m2, a2[j]), fminf(m1, a1[j]));
+                k0 = (a1[j] > m1) ? 4 * aq[j] + j : k0;
+                m1 = fmaxf(m1, a1[j]);
+            }
+        } else if (sstride & 1) {
             // odd stride (YOLOv7's 85-float rows): already conflict-free, a straight run without the wrap test
 #pragma unroll 8
             for (int k = 0; k < P.C; ++k) top2_update(cls[k], k, m1, m2, k0);
@@ -527,9 +559,9 @@ __device__ __forceinline__ void rows_scan_emit(const Plan &P, const LevelDesc &l
 }
 
 __global__ void __launch_bounds__(kRowsTile) k_filter_rows(const __grid_constant__ Plan P, uint64_t *__restrict__ keys,
-                                                           int64_t key_cap, int32_t *__restrict__ counts)
+                                                           int64_t key_cap, int32_t *__restrict__ counts, int flags)
 {
-    extern __shared__ float tile[];
+    extern __shared__ __align__(128) float tile[];
     const int img = blockIdx.x;  // image fastest: see k_filter_planes
     const int t = blockIdx.y;
     int l = 0;
@@ -548,12 +580,25 @@ __global__ void __launch_bounds__(kRowsTile) k_filter_rows(const __grid_constant
     // (below) instead of padding.  Odd shapes: scalar loads into a tile padded to an odd stride.
     const bool dense = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && ((nfl & 3) == 0);
     const int sstride = dense ? rw : (rw | 1);
-    if (dense) {
+    if (dense && !(flags & 1)) {
         const uint32_t dst = smem_u32(tile);
         const int nv = nfl >> 2;
         for (int i = threadIdx.x; i < nv; i += kRowsTile) cp_async16(dst + 16u * i, src + 4 * i);
         cp_async_commit();
         cp_async_wait<0>();
+    } else if (dense) {
+        // the tile is one contiguous block: ONE bulk copy of the TMA engine (cp.async.bulk -> mbarrier complete_tx) issued
+        // by thread 0 instead of 20 cp.async per thread
+        __shared__ __align__(8) uint64_t bar;
+        const uint32_t b32 = smem_u32(&bar);
+        if (threadIdx.x == 0) {
+            mbar_init(b32, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(b32, static_cast<uint32_t>(nfl) * 4u);
+            bulk_g2s(smem_u32(tile), src, static_cast<uint32_t>(nfl) * 4u, b32);
+        }
+        __syncthreads();   // the barrier is initialised before anybody polls it
+        mbar_wait(b32, 0u);
     } else {
         for (int e = threadIdx.x; e < nfl; e += kRowsTile) {
             const int row = e / rw, col = e - row * rw;
@@ -562,11 +607,13 @@ __global__ void __launch_bounds__(kRowsTile) k_filter_rows(const __grid_constant
     }
     __syncthreads();
 
-    rows_scan_emit(P, lv, img, tile, sstride, nrows, r0, static_cast<int>(threadIdx.x), keys, key_cap, counts);
+    rows_scan_emit(P, lv, img, tile, sstride, nrows, r0, static_cast<int>(threadIdx.x), keys, key_cap, counts, (flags & 2) != 0);
 }
 
+#ifdef YSB_PROFILING_VARIANTS
 // -------------------------------------------------------------------------------------------------------
-// rows layout, persistent ring version (the default whenever the tensors are 16-byte aligned -- every reference layout).
+// rows layout, persistent ring version (profiling build, YSB_ROWS_RING=1; measured SLOWER than k_filter_rows: 8 scanning
+// warps per SM cannot hide the shared-memory latency of the top-2 scan -- RetinaNet b=64 0.447 vs 0.324 ms).
 // A tile of 128 rows is ONE contiguous block of memory (40-44 KB), i.e. one bulk copy of the TMA engine
 // (cp.async.bulk -> mbarrier complete_tx): a CTA keeps kRingStages tiles in flight / under the scan, thread 0 re-arms a
 // stage as soon as the CTA has finished reading it.  Against k_filter_rows (one tile per CTA: ~300 CTA launches per SM
@@ -661,6 +708,8 @@ __global__ void __launch_bounds__(kRowsTile) k_filter_rows_ring(const __grid_con
         }
     }
 }
+
+#endif  // YSB_PROFILING_VARIANTS
 
 // -------------------------------------------------------------------------------------------------------
 // mutil_label: true -- one record per (candidate, class) whose score reaches the class threshold
@@ -801,6 +850,16 @@ cudaError_t launch_filter(const Plan &P, int vec, uint64_t *d_keys, int64_t key_
             // every level 128-bit loadable (the common case): 9 loads of 128 bits in flight per thread (YOLOv5 / YOLOX:
             // 80 classes + objectness = 9 batches of 9), 76 registers, 6 CTAs of 128 threads per SM
             const dim3 gv4(P.batch, (P.units_per_img + 127) / 128);
+#ifdef YSB_PROFILING_VARIANTS
+            {   // profiling build: YSB_K1_CARVEOUT=<percent of the SM's shared memory> as the kernel's preferred carve-out
+                static int pct = -2;
+                if (pct == -2) { const char *ev = getenv("YSB_K1_CARVEOUT"); pct = ev ? atoi(ev) : -1; }
+                if (pct >= 0) {
+                    e = cudaFuncSetAttribute(k_filter_planes_v4<9, 128, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+                    if (e != cudaSuccess) return e;
+                }
+            }
+#endif
             k_filter_planes_v4<9, 128, 6><<<gv4, 128, 0, stream>>>(P, d_keys, key_cap, d_counts);
         } else if (vec == 1) {
             const dim3 grid(P.batch, (P.units_per_img + 255) / 256);
@@ -813,9 +872,12 @@ cudaError_t launch_filter(const Plan &P, int vec, uint64_t *d_keys, int64_t key_
         }
     } else {
         const size_t smem = static_cast<size_t>(kRowsTile) * (P.row_w_in | 1) * sizeof(float);
+#ifdef YSB_PROFILING_VARIANTS
         // persistent ring kernel when two CTAs with kRingStages tiles each fit an SM and the tensors allow bulk copies
         // (16-byte aligned bases, image strides that keep every image's first row 16-byte aligned)
-        bool ring_ok = kRingStages * smem <= 110u * 1024u;
+        static int ring_env = -1;
+        if (ring_env < 0) { const char *ev = getenv("YSB_ROWS_RING"); ring_env = ev ? atoi(ev) : 0; }
+        bool ring_ok = ring_env != 0 && kRingStages * smem <= 110u * 1024u;
         for (int l = 0; l < P.L && ring_ok; ++l)
             ring_ok = (reinterpret_cast<uintptr_t>(P.lv[l].p0) & 15u) == 0 &&
                       ((static_cast<long long>(P.lv[l].img_rows) * P.row_w_in) & 3) == 0;
@@ -830,12 +892,25 @@ cudaError_t launch_filter(const Plan &P, int vec, uint64_t *d_keys, int64_t key_
             k_filter_rows_ring<<<static_cast<unsigned>(total < slots ? total : slots), kRowsTile, rsmem, stream>>>(P, d_keys, key_cap, d_counts);
             return cudaGetLastError();
         }
+#endif
         if (smem > 48 * 1024) {
             e = cudaFuncSetAttribute(k_filter_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
             if (e != cudaSuccess) return e;
         }
         const dim3 grid(P.batch, P.units_per_img);
-        k_filter_rows<<<grid, kRowsTile, smem, stream>>>(P, d_keys, key_cap, d_counts);
+        // Staging (bit 0): one bulk copy per tile for rows with an even float stride (RetinaNet, 84-float decoded rows),
+        // cp.async for odd strides (YOLOv7's 85-float rows).  Measured in the 4-lane pipeline on B200: RetinaNet b=64
+        // 207.5 k -> 214 k images/s with the bulk copy (three A/B pairs), YOLOv7 b=64 634 k -> 610 k.  Bit 1 (128-bit
+        // shared loads + four scan chains) measured neutral (208.7 k / 213.1 k) and is only reachable in profiling builds.
+        int flags = (P.row_w_in & 1) ? 0 : 1;
+#ifdef YSB_PROFILING_VARIANTS
+        {
+            static int fenv = -2;
+            if (fenv == -2) { const char *ev = getenv("YSB_ROWS_FLAGS"); fenv = ev ? atoi(ev) : -1; }
+            if (fenv >= 0) flags = fenv;
+        }
+#endif
+        k_filter_rows<<<grid, kRowsTile, smem, stream>>>(P, d_keys, key_cap, d_counts, flags);
     }
     return cudaGetLastError();
 }

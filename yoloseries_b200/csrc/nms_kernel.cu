@@ -35,6 +35,9 @@ constexpr int kDigitBits = 11;
 constexpr int kBins = 1 << kDigitBits;
 constexpr int kChunk = 128;         // candidates resolved per step of the greedy walk
 constexpr int kChunkWords = kChunk / 32;
+// class buckets (cls & (buckets - 1)) of the kept-slot / chunk-slot bit masks of the walk; sized so that the masks fit the
+// shared arrays they alias (NmsSmem)
+template <int KEEP> constexpr int kMaskBuckets = KEEP <= 320 ? 128 : 32;
 constexpr int kKeyBatch = 8;        // independent 64-bit key loads in flight per thread in the selection passes
 
 // Phase timestamps of image 0..63 (profiling builds only: -DYSB_K2_TIMING), read back by ysb_debug_k2_timing().
@@ -57,9 +60,19 @@ template <int KEEP>
 struct NmsSmem {
     uint64_t keys[kTranche];
     float4 raw[kTranche];          // raw boxes of the tranche entries; post-filter: offset boxes of a survivor block
-    float area[kTranche];          // post-filter: areas of the offset boxes
+    // The walk's class-bucket masks live in arrays only the post-filter uses: the footprint must stay below the 100 KB
+    // shared-memory carve-out step.  With the masks as separate fields (101 KB -> 132 KB carve-out, 32 KB less L1 for the
+    // in-flight loads of the filter CTAs that share the SM) the 4-lane pipeline lost 11 % (YOLOv5s b=64 745 k -> 660 k
+    // images/s, YOLOX b=256 1.93 M -> 1.75 M; aliased: 755 k / 2.02 M, A/B on one box).
+    union {
+        float area[kTranche];                                          // post-filter: areas of the offset boxes
+        uint32_t kept_mask[kMaskBuckets<KEEP>][(KEEP + 31) / 32];      // walk: kept slots holding a box of the bucket
+    };
     uint32_t hist[kBins];          // selection histograms; post-filter: class bucket bounds and cursors
-    uint16_t order[kTranche];      // post-filter: survivor indices sorted by class
+    union {
+        uint16_t order[kTranche];                                      // post-filter: survivor indices sorted by class
+        uint32_t chunk_mask[kMaskBuckets<KEEP>][kChunkWords];          // walk: chunk slots holding a candidate of the bucket
+    };
     float2 kept_x[KEEP];
     float2 kept_y[KEEP];
     float kept_a[KEEP];
@@ -74,6 +87,7 @@ struct NmsSmem {
     uint32_t chunk_pred[kChunk][kChunkWords];  // row j: earlier candidates i < j of the chunk that suppress j
     uint32_t keep_words[kChunkWords];
     uint8_t chunk_alive[kChunk];
+    int run_lo, run_hi, run_bad;   // x-span (order-preserving ints) of every box decoded so far; a non-finite one was seen
     uint32_t warp_tmp[32];
     int n_sel;
     int sel_digit;
@@ -379,9 +393,14 @@ __device__ __forceinline__ const Plan &pass_of(const Plan &P, const ExtraPasses 
 // boxes per DRAM round trip.  Every other layout: one thread per box.
 template <bool ARRAY, typename EXTRA, int THREADS, int KEEP>
 __device__ __forceinline__ void decode_boxes(NmsSmem<KEEP> &S, const Plan &P, const EXTRA &X, const ArrayArgs &aa, int img,
-                                             int from, int upto)
+                                             int from, int upto, int &lo_x, int &hi_x, bool &bad)
 {
     const int tid = threadIdx.x;
+    auto span = [&](const float4 &b) {   // this thread's share of the x-span of the decoded boxes
+        bad = bad || !(fabsf(b.x) <= 3.0e38f) || !(fabsf(b.z) <= 3.0e38f);
+        lo_x = min(lo_x, float_ordered(b.x));
+        hi_x = max(hi_x, float_ordered(b.z));
+    };
     if (!ARRAY && P.family == YSB_YOLOV8 && P.input_kind == YSB_INPUT_RAW_HEADS) {
         for (int i0 = from; i0 < upto; i0 += THREADS / 4) {
             const int i = i0 + (tid >> 2), side = tid & 3;
@@ -398,7 +417,9 @@ __device__ __forceinline__ void decode_boxes(NmsSmem<KEEP> &S, const Plan &P, co
             if (ok && side == 0) {
                 int c2 = static_cast<int>(key_cand(S.keys[i]));
                 const Plan &Q = pass_of(P, X, c2);
-                S.raw[i] = tta_undo(Q, v8_box_from_sides(Q, c2, s0, s1, s2, s3));
+                const float4 b = tta_undo(Q, v8_box_from_sides(Q, c2, s0, s1, s2, s3));
+                S.raw[i] = b;
+                span(b);
             }
         }
     } else {
@@ -408,7 +429,9 @@ __device__ __forceinline__ void decode_boxes(NmsSmem<KEEP> &S, const Plan &P, co
                 S.raw[i] = __ldg(aa.boxes + cand);
             } else {
                 const Plan &Q = pass_of(P, X, cand);
-                S.raw[i] = candidate_xyxy(Q, img, cand);
+                const float4 b = candidate_xyxy(Q, img, cand);
+                S.raw[i] = b;
+                span(b);
             }
         }
     }
@@ -457,6 +480,13 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
     // postprocess_bbox runs only for 1 < M < 3000 (FCOS: <= 300), trainer/eval_yolov5.py:306-307
     const bool window = !ARRAY && P.postprocess_bbox && M > 1 && M < P.window_hi;
 
+    // class-bucket masks of the walk (phase A / B below); the selection passes that follow contain the barriers that
+    // order this initialisation before the first use
+    if (!ARRAY) {
+        for (int i = tid; i < kMaskBuckets<KEEP> * ((KEEP + 31) / 32); i += THREADS) (&S.kept_mask[0][0])[i] = 0u;
+        for (int i = tid; i < kMaskBuckets<KEEP> * kChunkWords; i += THREADS) (&S.chunk_mask[0][0])[i] = 0u;
+        if (tid == 0) { S.run_lo = 0x7fffffff; S.run_hi = static_cast<int>(0x80000000u); S.run_bad = 0; }
+    }
     int kept = 0, processed = 0, n_tranche = 0, decoded_upto = 0;
     bool whole = false;   // the (single) tranche in shared memory holds every survivor
     uint64_t last_lo = 0; // lower bound of the last tranche's normalised keys
@@ -508,11 +538,30 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
                 // one round of (candidate, side) threads covers are decoded ahead of the walk
                 const bool dfl = !ARRAY && P.family == YSB_YOLOV8 && P.input_kind == YSB_INPUT_RAW_HEADS;
                 const int upto = min(n_use, decoded_upto + (dfl ? max(THREADS / 4, kChunk) : THREADS));
-                decode_boxes<ARRAY, EXTRA, THREADS, KEEP>(S, P, X, aa, img, decoded_upto, upto);
+                int d_lo = 0x7fffffff, d_hi = static_cast<int>(0x80000000u);
+                bool d_bad = false;
+                decode_boxes<ARRAY, EXTRA, THREADS, KEEP>(S, P, X, aa, img, decoded_upto, upto, d_lo, d_hi, d_bad);
                 decoded_upto = upto;
+                if (!ARRAY) {
+                    d_lo = __reduce_min_sync(0xffffffffu, d_lo);
+                    d_hi = __reduce_max_sync(0xffffffffu, d_hi);
+                    d_bad = __any_sync(0xffffffffu, d_bad);
+                    if ((tid & 31) == 0) {
+                        atomicMin(&S.run_lo, d_lo);
+                        atomicMax(&S.run_hi, d_hi);
+                        if (d_bad) S.run_bad = 1;
+                    }
+                }
                 __syncthreads();
             }
             K2_ACC(8);
+            // Class-aware walk: while every box seen so far is finite and the boxes span at most 4095 px in x, boxes of
+            // different classes are disjoint once offset (see the post-filter below for the bound), i.e. a candidate can
+            // only be suppressed by boxes of its own class -- found through per-class-bucket bit masks of the kept slots
+            // and of the chunk slots instead of testing every pair.  Buckets are cls & 127 (& 31): classes sharing a bucket only
+            // cost extra pair tests, the tests themselves are the exact ones.  Anything else: all pairs, as before.
+            const bool cls_fast = !ARRAY && P.class_aware && thr.positive && !S.run_bad &&
+                                  __fsub_rn(ordered_float(S.run_hi), ordered_float(S.run_lo)) <= 4095.0f;
             const int j = tid / TPC, sub = tid % TPC;
             const unsigned group = ((1u << TPC) - 1u) << ((tid & 31) / TPC * TPC);
             // phase A: TPC threads per candidate test it against the kept list
@@ -526,7 +575,21 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
                     score = key_score(key);
                     const float off = P.class_aware ? __fmul_rn(static_cast<float>(key_cls(key)), 4096.0f) : 0.0f;
                     ob = make_offbox(S.raw[c0 + j], off);
-                    sup = any_hit_strided<ARRAY>(kept_box, sub, TPC, kept, ob, thr, aa);
+                    if (cls_fast) {
+                        const uint32_t *km = S.kept_mask[key_cls(key) & (kMaskBuckets<KEEP> - 1)];
+                        const int nw = (kept + 31) >> 5;
+                        for (int wd = sub; wd < nw; wd += TPC) {
+                            uint32_t m = km[wd];
+                            while (m) {
+                                const int i = 32 * wd + __ffs(m) - 1;
+                                m &= m - 1u;
+                                sup |= pair_hit<ARRAY>(kept_box, i, ob, thr, aa);
+                            }
+                        }
+                        if (sub == 0) atomicOr(&S.chunk_mask[key_cls(key) & (kMaskBuckets<KEEP> - 1)][j >> 5], 1u << (j & 31));
+                    } else {
+                        sup = any_hit_strided<ARRAY>(kept_box, sub, TPC, kept, ob, thr, aa);
+                    }
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, sup);
                 if (sub == 0) {
@@ -543,7 +606,26 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
                 uint32_t w[kChunkWords];
 #pragma unroll
                 for (int c = 0; c < kChunkWords; ++c) w[c] = 0u;
-                if (j < cn && S.chunk_alive[j]) {
+                if (cls_fast) {
+                    if (j < cn && S.chunk_alive[j]) {
+                        const OffBox bj = soa_load(chunk_box, j);
+                        const uint32_t *cm = S.chunk_mask[key_cls(S.keys[c0 + j]) & (kMaskBuckets<KEEP> - 1)];
+                        for (int wd = sub; wd <= (j >> 5); wd += TPC) {
+                            uint32_t m = cm[wd];
+                            if (wd == (j >> 5)) m &= (1u << (j & 31)) - 1u;   // earlier candidates only
+                            while (m) {
+                                const int i = 32 * wd + __ffs(m) - 1;
+                                m &= m - 1u;
+                                if (!S.chunk_alive[i]) continue;
+                                if (pair_hit<ARRAY>(chunk_box, i, bj, thr, aa)) {
+#pragma unroll
+                                    for (int c = 0; c < kChunkWords; ++c)   // (static register index: no local memory)
+                                        w[c] |= (i >> 5) == c ? 1u << (i & 31) : 0u;
+                                }
+                            }
+                        }
+                    }
+                } else if (j < cn && S.chunk_alive[j]) {
                     const OffBox bj = soa_load(chunk_box, j);
                     const bool fast = thr.positive && (!ARRAY || aa.iou_kind == YSB_IOU_NUMBA_F64MIX);
                     for (int i0 = sub; i0 < j; i0 += 4 * TPC) {
@@ -660,8 +742,12 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
                         } else {
                             S.kept_key[at] = S.keys[c0 + tid];
                             S.kept_raw[at] = S.raw[c0 + tid];
+                            // (maintained even while the walk tests all pairs: cheap, and the span can only grow)
+                            atomicOr(&S.kept_mask[key_cls(S.keys[c0 + tid]) & (kMaskBuckets<KEEP> - 1)][at >> 5], 1u << (at & 31));
                         }
                     }
+                    // the chunk's class-bucket mask is all zero again for the next chunk
+                    if (!ARRAY && cls_fast && tid < cn) S.chunk_mask[key_cls(S.keys[c0 + tid]) & (kMaskBuckets<KEEP> - 1)][tid >> 5] = 0u;
                 }
             }
             kept += added;
@@ -706,15 +792,17 @@ k_select_nms(const __grid_constant__ Plan P, const __grid_constant__ EXTRA X, co
             k_lo = min(k_lo, float_ordered(rb.x));
             k_hi = max(k_hi, float_ordered(rb.z));
         }
+        int pf_lo = 0, pf_hi = 0;   // (decode_boxes' span outputs: unused here, the block computes its own below)
+        bool pf_bad = false;
         for (int b0 = 0; b0 < total; b0 += kTranche) {
             const int mm = min(kTranche, total - b0);
             __syncthreads();
             if (!resident) {
                 for (int i = tid; i < mm; i += THREADS) S.keys[i] = __ldg(keys + b0 + i);
                 __syncthreads();
-                decode_boxes<false, EXTRA, THREADS, KEEP>(S, P, X, aa, img, 0, mm);
+                decode_boxes<false, EXTRA, THREADS, KEEP>(S, P, X, aa, img, 0, mm, pf_lo, pf_hi, pf_bad);
             } else if (decoded_upto < mm) {
-                decode_boxes<false, EXTRA, THREADS, KEEP>(S, P, X, aa, img, decoded_upto, mm);
+                decode_boxes<false, EXTRA, THREADS, KEEP>(S, P, X, aa, img, decoded_upto, mm, pf_lo, pf_hi, pf_bad);
             }
             __syncthreads();
             if (!P.merge_boxes) {
