@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--family", default="")
     ap.add_argument("--img", type=int, default=0)
     ap.add_argument("--dist", default="dense", choices=["dense", "sparse", "crowd"])
-    ap.add_argument("--lanes", type=int, default=4, help="batches in flight per rank (one CUDA stream each)")
+    ap.add_argument("--lanes", type=int, default=0, help="batches in flight per rank, one CUDA stream each (0: the package default, 4 on one GPU, 6 with peers)")
     ap.add_argument("--graph", type=int, default=-1, help="replay captured CUDA graphs (-1: when batch <= 16)")
     ap.add_argument("--gather", default="auto", choices=["auto", "p2p", "nccl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -349,7 +349,7 @@ def run_ours(args):
             self.batch, self.dist_name = batch, dist_name
             self.heads = synth.make_heads(args.family, batch, args.img, args.img, 80, dist_name, seed, dev)
             self.flat = flatten_heads(args.family, self.heads)
-            self.spp = ShardedPostProcessor(args.family, hyp, batch, args.img, args.img, anchors=anchors, lanes=args.lanes,
+            self.spp = ShardedPostProcessor(args.family, hyp, batch, args.img, args.img, anchors=anchors, lanes=args.lanes or None,
                                             gather=args.gather, graph=graph)
 
         def fork(self):
@@ -359,7 +359,8 @@ def run_ours(args):
         def measure(self, steps, warmup, events=False):
             """Exactly `steps` timed steps bracketed by barrier + synchronize; device time, max over ranks."""
             spp = self.spp
-            for _ in range(max(warmup, 3)):
+            # (with CUDA graphs every lane captures its launch sequence on its second use: all of that stays untimed)
+            for _ in range(max(warmup, 3, spp.lanes + 2 if spp.graph else 0)):
                 spp.submit(self.heads, sync_input=False)
             spp.drain()
             sync_all()

@@ -183,7 +183,8 @@ class DetectionGather:
 
 
 class ShardedPostProcessor:
-    """The multi-GPU path as an API: every rank post-processes its own image shard, ``lanes`` batches in flight, and the
+    """The multi-GPU path as an API: every rank post-processes its own image shard, ``lanes`` batches in flight (default
+    4, 6 with peers), and the
     kept detections of ALL ranks end up on EVERY rank.
 
         spp = ShardedPostProcessor("yolov5", hyp, batch=8, img_h=640, img_w=640, anchors=anchors)
@@ -199,7 +200,7 @@ class ShardedPostProcessor:
     A ticket's buffers are reused ``lanes`` submissions later.
     """
 
-    def __init__(self, family, hyp, batch, img_h, img_w, anchors=None, lanes=4, group=None, gather="auto", graph=None,
+    def __init__(self, family, hyp, batch, img_h, img_w, anchors=None, lanes=None, group=None, gather="auto", graph=None,
                  compute_metric=False, device=None):
         from .engine import PostProcessor
         self.family, self.batch, self.img_h, self.img_w = family, int(batch), int(img_h), int(img_w)
@@ -207,7 +208,10 @@ class ShardedPostProcessor:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.lanes = max(1, int(lanes))
+        # batches in flight: 4 hide the NMS kernel behind the filter kernels of the next batches on one GPU; with peers a
+        # lane also stays busy until every rank's rows have landed, which 6 lanes cover (B200 x2, YOLOv5s b=64: 4 lanes
+        # 0.0944 ms per step, 6 lanes 0.0891 = the slower GPU's own pace, 8 lanes 0.0895; one GPU: 0.0847 / 0.0887)
+        self.lanes = max(1, int(lanes)) if lanes else (4 if self.world == 1 else 6)
         self.pp = PostProcessor(family, hyp, anchors=anchors, compute_metric=compute_metric)
         self.lib = _lib.load()
         self.max_det = int(hyp["max_predictions_per_img"])
