@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--family", default="")
     ap.add_argument("--img", type=int, default=0)
     ap.add_argument("--dist", default="dense", choices=["dense", "sparse", "crowd"])
-    ap.add_argument("--lanes", type=int, default=0, help="batches in flight per rank, one CUDA stream each (0: the package default, 4 on one GPU, 6 with peers)")
+    ap.add_argument("--lanes", type=int, default=0, help="batches in flight per rank, one CUDA stream each (0: the package default -- 4 on one GPU, 6 with peers, 8 for batches below 64 images)")
     ap.add_argument("--graph", type=int, default=-1, help="replay captured CUDA graphs (-1: when batch <= 16)")
     ap.add_argument("--gather", default="auto", choices=["auto", "p2p", "nccl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -507,7 +507,7 @@ def run_ours(args):
     # ---- the same shape on the other input distributions, and BASELINE's "batch 64 sharded over N GPUs" -----------------
     extras = {}
     if not args.no_extras:
-        ex_steps = max(10, min(args.steps, 30))
+        ex_steps = max(10, min(args.steps, 200))
         if args.family in ("yolov5", "yolov7") and args.dist == "dense":
             dists = {}
             for dname in ("sparse", "crowd"):

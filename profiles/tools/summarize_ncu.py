@@ -25,12 +25,16 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__cycles_active.avg", "sm__cycles_elapsed.max",
         "lts__t_sector_hit_rate.pct", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "launch__shared_mem_per_block_dynamic", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"]
-for name, pat in (("filter", "k_filter_planes"), ("nms", "k_select_nms")):
+import os
+for name, pat in (("filter", "k_filter_planes"), ("nms", "k_select_nms"), ("nms_c3", "k_select_nms"), ("rows", "k_filter_rows")):
+    if not os.path.exists(f"gpurun_out/prof_{name}_{tag}.ncu-rep"):
+        continue
     txt = subprocess.run(["ncu", "-i", f"gpurun_out/prof_{name}_{tag}.ncu-rep", "--page", "raw", "--csv"],
                          capture_output=True, text=True).stdout
     rr = list(csv.reader(txt.splitlines()))
     h = rr[0]
-    lines = [f"# ncu --set full --clock-control none --import-source on -k regex:{pat} -s 3 -c 2  python bench.py --steps 2 --warmup 3 --no-cpu-baseline",
+    cfg = {"nms_c3": " --config c3", "rows": " --config c4"}.get(name, "")
+    lines = [f"# ncu --set full --clock-control none --import-source on -k regex:{pat} -s 3 -c 2  python bench.py{cfg} --steps 2 --warmup 3 --no-cpu-baseline",
              f"# kernel: {rr[2][h.index('Kernel Name')][:100]}  grid {rr[2][h.index('Grid Size')]} block {rr[2][h.index('Block Size')]}", ""]
     for w in want:
         if w in h:

@@ -358,6 +358,45 @@ def test_boxes_wider_than_the_class_offset():
                 np.testing.assert_array_equal(idx[i], w.cand_index)
 
 
+@pytest.mark.parametrize("threads", [0, 512, 1024])
+def test_class_bucket_walk_switches_to_all_pairs_mid_image(threads):
+    """The greedy walk tests a candidate only against kept / chunk boxes of its own class bucket (cls & 127) while every
+    decoded box is finite and the boxes span <= 4095 px in x; the first wider box -- here they only appear in the LATER
+    tranches, among the low scores -- switches the image to all pairs, where classes interact through the reference's
+    cls * 4096 offset.  150 classes: several classes share a bucket.  Heavy crowding: the walk needs several tranches."""
+    from yoloseries_b200 import _lib
+    rng = np.random.default_rng(11)
+    n, C, b = 2900, 150, 2                                             # < 3000: the postprocess_bbox count filter runs too
+    hyp = oracle.default_hyp(num_class=C, conf_threshold=0.0, cls_threshold=0.0, iou_threshold=0.45)
+    centres = rng.uniform(80, 560, size=(b, 40, 2))
+    dec = np.zeros((b, n, 5 + C), dtype=np.float32)
+    pick = rng.integers(0, 40, size=(b, n))
+    dec[..., 0:2] = np.take_along_axis(centres, pick[..., None].repeat(2, -1), 1) + rng.normal(0, 4, size=(b, n, 2))
+    dec[..., 2:4] = rng.uniform(40, 90, size=(b, n, 2))
+    dec[..., 4] = rng.uniform(0.35, 1.0, size=(b, n))
+    cls = (pick * 7 + rng.integers(0, 2, size=(b, n)) * 128) % C      # classes c and c + 128 land in one bucket
+    dec[..., 5:] = rng.uniform(0.0, 0.2, size=(b, n, C))
+    np.put_along_axis(dec[..., 5:], cls[..., None], rng.uniform(0.8, 1.0, size=(b, n, 1)).astype(np.float32), 2)
+    low = np.argsort(dec[..., 4], axis=1)[:, :900]                    # the 900 lowest objectness values of each image
+    for i in range(b):
+        wide = low[i, rng.choice(900, size=60, replace=False)]
+        dec[i, wide, 2] = rng.uniform(4500, 14000, size=60)
+        dec[i, wide[:20], 0] = rng.uniform(-400, 0, size=20)
+    want = oracle.evaluator_nms("yolov5", dec, hyp)
+    lib = _lib.load()
+    try:
+        assert lib.ysb_set_nms_cta_threads(threads) == 0
+        pp = _pp("yolov5", hyp)
+        rows, idx = pp.to_list(pp.run(torch.from_numpy(dec).cuda(), 640, 640, decoded=True), as_numpy=True, with_index=True)
+    finally:
+        lib.ysb_set_nms_cta_threads(0)
+    for i, w in enumerate(want):
+        assert w.rows is not None and rows[i] is not None
+        np.testing.assert_array_equal(rows[i], w.rows)
+        np.testing.assert_array_equal(idx[i], w.cand_index)
+        assert w.cand_index.max() >= 0
+
+
 def test_sigmoid_reciprocal_is_frcp_rn():
     """sigmoid_ref's spelled-out reciprocal == __frcp_rn for every float in [1, +inf] (1.07e9 bit patterns), and the
     branch-free batch variant of the decode kernel agrees below 2^126 and flags everything at or above it."""

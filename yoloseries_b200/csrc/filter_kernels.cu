@@ -893,15 +893,13 @@ cudaError_t launch_filter(const Plan &P, int vec, uint64_t *d_keys, int64_t key_
             return cudaGetLastError();
         }
 #endif
-        if (smem > 48 * 1024) {
-            e = cudaFuncSetAttribute(k_filter_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-            if (e != cudaSuccess) return e;
-        }
         const dim3 grid(P.batch, P.units_per_img);
         // Staging (bit 0): one bulk copy per tile for rows with an even float stride (RetinaNet, 84-float decoded rows),
         // cp.async for odd strides (YOLOv7's 85-float rows).  Measured in the 4-lane pipeline on B200: RetinaNet b=64
         // 207.5 k -> 214 k images/s with the bulk copy (three A/B pairs), YOLOv7 b=64 634 k -> 610 k.  Bit 1 (128-bit
         // shared loads + four scan chains) measured neutral (208.7 k / 213.1 k) and is only reachable in profiling builds.
+        // Two threads per row (256-thread CTAs, halves merged by shuffle) measured 1.7x SLOWER (RetinaNet 216 k -> 124 k,
+        // YOLOv7 642 k -> 366 k) and was removed.
         int flags = (P.row_w_in & 1) ? 0 : 1;
 #ifdef YSB_PROFILING_VARIANTS
         {
@@ -910,6 +908,10 @@ cudaError_t launch_filter(const Plan &P, int vec, uint64_t *d_keys, int64_t key_
             if (fenv >= 0) flags = fenv;
         }
 #endif
+        if (smem > 48 * 1024) {
+            e = cudaFuncSetAttribute(k_filter_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (e != cudaSuccess) return e;
+        }
         k_filter_rows<<<grid, kRowsTile, smem, stream>>>(P, d_keys, key_cap, d_counts, flags);
     }
     return cudaGetLastError();

@@ -183,8 +183,8 @@ class DetectionGather:
 
 
 class ShardedPostProcessor:
-    """The multi-GPU path as an API: every rank post-processes its own image shard, ``lanes`` batches in flight (default
-    4, 6 with peers), and the
+    """The multi-GPU path as an API: every rank post-processes its own image shard, ``lanes`` batches in flight (default:
+    4, 6 with peers, 8 for batches below 64 images), and the
     kept detections of ALL ranks end up on EVERY rank.
 
         spp = ShardedPostProcessor("yolov5", hyp, batch=8, img_h=640, img_w=640, anchors=anchors)
@@ -208,10 +208,17 @@ class ShardedPostProcessor:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        # batches in flight: 4 hide the NMS kernel behind the filter kernels of the next batches on one GPU; with peers a
-        # lane also stays busy until every rank's rows have landed, which 6 lanes cover (B200 x2, YOLOv5s b=64: 4 lanes
-        # 0.0944 ms per step, 6 lanes 0.0891 = the slower GPU's own pace, 8 lanes 0.0895; one GPU: 0.0847 / 0.0887)
-        self.lanes = max(1, int(lanes)) if lanes else (4 if self.world == 1 else 6)
+        # Batches in flight.  Large batches: 4 hide the NMS kernel behind the filter kernels of the next batches; with peers
+        # a lane also stays busy until every rank's rows have landed, which 6 lanes cover.  Batches below 64 images leave
+        # SMs idle per launch and want 8.  Measured on B200 (YOLOv5s 640, images/s): b=64 4 / 6 lanes 738 k / 722 k on one
+        # GPU, 0.0944 / 0.0891 ms per step on two; b=32 603 k / 694 k (4 / 6); b=16 550 k / 618 k / 654 k (4 / 6 / 8);
+        # YOLOv5x-1280 b=16 174.5 k / 185.2 k / 187.7 k; b=8 476 k / 480 k / 485 k.
+        if lanes:
+            self.lanes = max(1, int(lanes))
+        elif self.batch < 64:
+            self.lanes = 8
+        else:
+            self.lanes = 4 if self.world == 1 else 6
         self.pp = PostProcessor(family, hyp, anchors=anchors, compute_metric=compute_metric)
         self.lib = _lib.load()
         self.max_det = int(hyp["max_predictions_per_img"])
