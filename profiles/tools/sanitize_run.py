@@ -35,6 +35,33 @@ for fam, img in (("yolov5", 128), ("yolov7", 128), ("yolox", 96), ("yolov8", 64)
         pp.decode_tta(passes, (img, img))
     print(fam, "ok", flush=True)
 
+# both CTA flavours of the NMS kernel on multi-tranche inputs: a crowd (several tranches, class-bucket walk) and decoded rows
+# whose wide boxes switch the walk to all pairs mid-image (count filter active)
+from yoloseries_b200 import _lib  # noqa: E402
+lib = _lib.load()
+rng = np.random.default_rng(11)
+n, CC = 2900, 150
+dec = np.zeros((2, n, 5 + CC), dtype=np.float32)
+dec[..., 0:2] = rng.uniform(80, 560, size=(2, 40, 2))[:, rng.integers(0, 40, size=n)] + rng.normal(0, 4, size=(2, n, 2))
+dec[..., 2:4] = rng.uniform(40, 90, size=(2, n, 2))
+dec[..., 4] = rng.uniform(0.35, 1.0, size=(2, n))
+dec[..., 5:] = rng.uniform(0.0, 1.0, size=(2, n, CC))
+dec[:, -60:, 2] = rng.uniform(4500, 14000, size=(2, 60))
+dec[:, -60:, 4] *= 0.3
+for threads in (512, 1024):
+    lib.ysb_set_nms_cta_threads(threads)
+    hyp = synth.map_profile_hyp(num_class=80)
+    pp = PostProcessor("yolov5", hyp, anchors=torch.tensor(synth.V5_ANCHORS_PX))
+    for dist in ("crowd", "dense", "sparse"):
+        heads = synth.make_heads("yolov5", 2, 320, 320, 80, dist, seed=9, device="cuda")
+        pp.to_list(pp.run(heads, 320, 320))
+    hyp2 = synth.map_profile_hyp(num_class=CC)
+    hyp2.update(conf_threshold=0.0, cls_threshold=0.0, iou_threshold=0.45)
+    pp2 = PostProcessor("yolov5", hyp2, anchors=torch.tensor(synth.V5_ANCHORS_PX))
+    pp2.to_list(pp2.run(torch.from_numpy(dec).cuda(), 640, 640, decoded=True))
+    print("nms flavour", threads, "ok", flush=True)
+lib.ysb_set_nms_cta_threads(0)
+
 rng = np.random.default_rng(0)
 xy = rng.uniform(0, 300, size=(3000, 2)).astype(np.float32)
 wh = rng.uniform(4, 80, size=(3000, 2)).astype(np.float32)
