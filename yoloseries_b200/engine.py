@@ -515,8 +515,9 @@ class PostProcessor:
 
 class PipelinedPostProcessor:
     """Several batches in flight: batch i runs filter -> NMS on CUDA stream ``i % lanes`` with its own buffers, so the
-    latency-bound NMS kernel of one batch overlaps the HBM-bound filter kernel of the next ones (bench.py's default
-    mode; 4 lanes hide the NMS kernel completely at 64 images per batch).
+    NMS kernel of one batch overlaps the HBM-bound filter kernels of the next ones (the single-GPU form of
+    dist.ShardedPostProcessor, which bench.py runs; 4 lanes hide the NMS kernel completely at 64 images per batch, batches
+    below 64 images want 8).
 
         t = ppp.submit(heads, h, w)      # returns immediately
         dets = ppp.result(t)             # list[Tensor(K,6) | None], blocks on that batch only
