@@ -127,9 +127,13 @@ __device__ __forceinline__ bool decide_candidate(const Plan &P, float m1, float 
 }
 
 // Warp-aggregated append of up to VEC keys per thread (okm: bit j set when k[j] is a survivor).
+// ext_seen: the image's running score extrema (cnt[2], cnt[3]) as read EARLIER by the caller (kernel start: the load's
+// latency hides behind the scan; a stale value only means a redundant fire-and-forget atomicMax), or nullptr: read here,
+// issued before the slot reservation so that the two round trips overlap instead of adding up.
 template <int VEC>
 __device__ __forceinline__ void emit_keys(const uint64_t (&k)[VEC], unsigned okm, int npre, uint32_t smax_bits,
-                                          uint32_t smin_inv, uint64_t *keys_img, int64_t cap, int32_t *cnt, bool count_pre)
+                                          uint32_t smin_inv, uint64_t *keys_img, int64_t cap, int32_t *cnt, bool count_pre,
+                                          const uint2 *ext_seen = nullptr)
 {
     const unsigned lane = threadIdx.x & 31u;
     const int nk = __popc(okm);
@@ -149,11 +153,18 @@ __device__ __forceinline__ void emit_keys(const uint64_t (&k)[VEC], unsigned okm
     const uint32_t wmin = __reduce_max_sync(0xffffffffu, smin_inv);
     int base = 0;
     if (lane == 0) {
-        base = atomicAdd(cnt, total);
         // the running extrema rarely change after the first warps of an image: look before touching them
-        volatile unsigned int *ext = reinterpret_cast<volatile unsigned int *>(cnt + 2);
-        if (wmax > ext[0]) atomicMax(reinterpret_cast<unsigned int *>(cnt + 2), wmax);
-        if (wmin > ext[1]) atomicMax(reinterpret_cast<unsigned int *>(cnt + 3), wmin);
+        uint2 ext;
+        if (ext_seen) {
+            ext = *ext_seen;
+        } else {
+            const volatile unsigned int *e = reinterpret_cast<const volatile unsigned int *>(cnt + 2);
+            ext.x = e[0];
+            ext.y = e[1];
+        }
+        base = atomicAdd(cnt, total);
+        if (wmax > ext.x) atomicMax(reinterpret_cast<unsigned int *>(cnt + 2), wmax);
+        if (wmin > ext.y) atomicMax(reinterpret_cast<unsigned int *>(cnt + 3), wmin);
     }
     base = __shfl_sync(0xffffffffu, base, 0);
     const int64_t at = static_cast<int64_t>(base) + (incl - nk);
@@ -458,7 +469,7 @@ constexpr int kRowsTile = 128;
 // survivors.  Every thread of the warp must call (rows beyond nrows contribute nothing).
 __device__ __forceinline__ void rows_scan_emit(const Plan &P, const LevelDesc &lv, int img, const float *tile, int sstride,
                                                int nrows, int r0, int t, uint64_t *__restrict__ keys, int64_t key_cap,
-                                               int32_t *__restrict__ counts, bool vec4 = false)
+                                               int32_t *__restrict__ counts, bool vec4 = false, const uint2 *ext_seen = nullptr)
 {
     uint64_t out[1] = {0ull};
     unsigned okm = 0u;
@@ -555,7 +566,7 @@ __device__ __forceinline__ void rows_scan_emit(const Plan &P, const LevelDesc &l
         }
     }
     emit_keys<1>(out, okm, npre, smax_bits, smin_inv, keys + static_cast<int64_t>(img) * key_cap, key_cap,
-                 counts + img * 4, P.pre_kind == PRE_ANY_GT);
+                 counts + img * 4, P.pre_kind == PRE_ANY_GT, ext_seen);
 }
 
 __global__ void __launch_bounds__(kRowsTile) k_filter_rows(const __grid_constant__ Plan P, uint64_t *__restrict__ keys,
@@ -575,6 +586,9 @@ __global__ void __launch_bounds__(kRowsTile) k_filter_rows(const __grid_constant
     const int rw = P.row_w_in;
     const float *src = lv.p0 + (static_cast<size_t>(img) * lv.img_rows + r0) * rw;
     const int nfl = nrows * rw;
+    // the image's running score extrema, read now so that the load hides behind the staging copy (see emit_keys)
+    const volatile unsigned int *ext_p = reinterpret_cast<const volatile unsigned int *>(counts + img * 4 + 2);
+    const uint2 ext_seen = make_uint2(ext_p[0], ext_p[1]);
     // 16-byte aligned tiles (every reference layout): cp.async straight into a DENSE shared tile -- no register
     // staging, no per-element address math.  Rows with an even float stride are scanned with a per-thread rotation
     // (below) instead of padding.  Odd shapes: scalar loads into a tile padded to an odd stride.
@@ -607,7 +621,8 @@ __global__ void __launch_bounds__(kRowsTile) k_filter_rows(const __grid_constant
     }
     __syncthreads();
 
-    rows_scan_emit(P, lv, img, tile, sstride, nrows, r0, static_cast<int>(threadIdx.x), keys, key_cap, counts, (flags & 2) != 0);
+    rows_scan_emit(P, lv, img, tile, sstride, nrows, r0, static_cast<int>(threadIdx.x), keys, key_cap, counts, (flags & 2) != 0,
+                   &ext_seen);
 }
 
 #ifdef YSB_PROFILING_VARIANTS
