@@ -7,20 +7,25 @@
 // The reference runs the greedy loop over all M survivors (O(K*M), ~14 s per image at M = 25 k) and truncates to
 // max_det afterwards.  Greedy NMS is prefix-stable, so this kernel visits candidates in the reference's order
 // (score desc, candidate asc) and stops at max_det keeps:
-//   1. pick a score threshold that leaves the next ~500-1000 best keys: radix descent over shared-memory histograms of
-//      the normalised 64-bit keys -- of a strided SAMPLE of them when the image has many survivors (the exact gather
-//      that follows counts what the threshold really selects and falls back to the exact descent if it overflows),
-//   2. gather those keys (one pass over the image's key list), bitonic-sort them (registers + shuffles, shared memory
-//      only for strides >= 32), decode their boxes (4 channels each) from the head tensors as far as the walk gets,
-//   3. walk them 128 at a time: every candidate against the kept list (8 threads per candidate, 4 independent
-//      shared-memory loads in flight each), in-chunk predecessor masks, greedy resolution by one warp, append,
+//   1. pick a score threshold for the next tranche of best keys -- the FIRST tranche is sized for a sort with one element
+//      per thread (most images reach max_det inside it), later ones are larger: radix descent over shared-memory
+//      histograms of the normalised 64-bit keys -- of a strided SAMPLE of them when the image has many survivors (the exact
+//      gather that follows counts what the threshold really selects and falls back to the exact descent if it overflows),
+//   2. gather those keys (one pass over the image's key list, one shared-memory reservation per warp and 8 ballots),
+//      bitonic-sort them (registers + shuffles, shared memory only for strides >= 32), decode their boxes (4 channels
+//      each) from the head tensors as far as the walk gets,
+//   3. walk them 128 at a time: every candidate against the kept list, in-chunk predecessor masks, greedy resolution by
+//      one warp, append.  While all boxes seen are finite and span <= 4095 px in x, classes cannot interact through the
+//      reference's cls * 4096 offset, and a candidate is only tested against the kept / chunk boxes of its own class
+//      bucket (bit masks per bucket); otherwise against all of them (4-8 threads per candidate),
 //   4. if fewer than max_det boxes are kept and candidates remain, select the next tranche and continue,
 //   5. postprocess_bbox count filter / RetinaNet merge (streamed over ALL survivors in blocks, bucketed by class) /
 //      remove_small_boxes, ordered write of the rows -- to the caller's buffer or, in a multi-GPU detection gather, into
 //      every peer's receive slot over NVLink.
-// One CTA per image.  Two flavours of the CTA: 1024 threads (one image per SM: lowest latency, small batches) and 512
-// threads with <= 113 KB of shared memory (two images per SM: the barrier stalls of one overlap the work of the other;
-// batches larger than the SM count).
+// One CTA per image.  Two flavours of the CTA (launch_any): 1024 threads (lowest latency: small batches, YOLOv8's DFL
+// decode, very long key lists) and 512 threads (from 32 images up: half of the SM's registers stay free for the filter
+// CTAs of the next batches, and two CTAs fit an SM when there are more images than SMs).  The shared-memory footprint
+// (94 KB at max_det <= 320) is kept under the 100 KB carve-out step on purpose, see NmsSmem.
 #include <cstdlib>
 
 #include "ysb_internal.cuh"
