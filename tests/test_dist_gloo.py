@@ -45,3 +45,11 @@ def _worker(rank, world, port, batch, max_det):
 def test_gather_detections_gloo(world, batch):
     port = 29500 + (os.getpid() % 500) + world * 7 + batch
     mp.spawn(_worker, args=(world, port, batch, 12), nprocs=world, join=True)
+
+
+def test_default_lanes_follow_batch_and_world():
+    """Host-side choice of the batches in flight (dist.default_lanes): 4 on one GPU, 6 with peers, 8 below 64 images."""
+    from yoloseries_b200.dist import default_lanes
+    assert default_lanes(64, 1) == 4 and default_lanes(256, 1) == 4
+    assert default_lanes(64, 2) == 6 and default_lanes(64, 8) == 6
+    assert [default_lanes(b, w) for b in (1, 8, 16, 32, 63) for w in (1, 8)] == [8] * 10

@@ -95,6 +95,19 @@ def bind_to_gpu_numa(local_rank):
     return None
 
 
+def default_lanes(batch, world):
+    """Batches in flight per rank (one CUDA stream each) when the caller does not say.
+
+    Large batches: 4 hide the NMS kernel behind the filter kernels of the next batches; with peers a lane also stays busy
+    until every rank's rows have landed, which 6 lanes cover.  Batches below 64 images leave SMs idle per launch and want 8.
+    Measured on B200 (YOLOv5s 640, images/s): b=64 4 / 6 lanes 738 k / 722 k on one GPU, 0.0944 / 0.0891 ms per step on
+    two; b=32 603 k / 694 k (4 / 6); b=16 550 k / 618 k / 654 k (4 / 6 / 8); YOLOv5x-1280 b=16 174.5 k / 185.2 k / 187.7 k;
+    b=8 476 k / 480 k / 485 k."""
+    if int(batch) < 64:
+        return 8
+    return 4 if int(world) == 1 else 6
+
+
 class _DevicePointer:
     """``__cuda_array_interface__`` holder: a zero-copy torch view of memory the C ABI allocated."""
 
@@ -208,17 +221,7 @@ class ShardedPostProcessor:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        # Batches in flight.  Large batches: 4 hide the NMS kernel behind the filter kernels of the next batches; with peers
-        # a lane also stays busy until every rank's rows have landed, which 6 lanes cover.  Batches below 64 images leave
-        # SMs idle per launch and want 8.  Measured on B200 (YOLOv5s 640, images/s): b=64 4 / 6 lanes 738 k / 722 k on one
-        # GPU, 0.0944 / 0.0891 ms per step on two; b=32 603 k / 694 k (4 / 6); b=16 550 k / 618 k / 654 k (4 / 6 / 8);
-        # YOLOv5x-1280 b=16 174.5 k / 185.2 k / 187.7 k; b=8 476 k / 480 k / 485 k.
-        if lanes:
-            self.lanes = max(1, int(lanes))
-        elif self.batch < 64:
-            self.lanes = 8
-        else:
-            self.lanes = 4 if self.world == 1 else 6
+        self.lanes = max(1, int(lanes)) if lanes else default_lanes(self.batch, self.world)
         self.pp = PostProcessor(family, hyp, anchors=anchors, compute_metric=compute_metric)
         self.lib = _lib.load()
         self.max_det = int(hyp["max_predictions_per_img"])
